@@ -1,0 +1,27 @@
+// classify.h — host-visible launch API of classify.cu (internal to libclawker_gpu.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dev_tables.h"
+
+namespace clk {
+
+enum { LOADER_TMA_SW64 = 0, LOADER_TMA = 1, LOADER_DIRECT = 2 };
+
+struct LaunchInfo { uint32_t grid, block, smem; };
+
+// All launchers enqueue on `st` and return nullptr on success or a static error string.
+const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride, unsigned long long n, uint32_t flags,
+                         uint32_t *d_verdicts, cudaStream_t st, int loader, LaunchInfo *info);
+const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n, uint32_t flags,
+                          uint32_t *d_verdicts, cudaStream_t st, LaunchInfo *info);
+const char *launch_events(const DevTables &T, const clk_event *d_ev, unsigned long long n, uint32_t flags, uint32_t *d_verdicts,
+                          cudaStream_t st, LaunchInfo *info);
+const char *launch_dns_extract(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n,
+                               const uint32_t *d_verdicts, unsigned long long *d_block_sums, unsigned long long *d_pos,
+                               unsigned long long *d_total, clk_dns_update_rec *d_out, unsigned long long cap, cudaStream_t st);
+const char *launch_counters_export(const DevTables &T, clk_metric *d_block, cudaStream_t st);
+const char *launch_counters_clear(const DevTables &T, cudaStream_t st);
+const char *launch_counters_import(const DevTables &T, const clk_metric *d_blocks, unsigned long long rows, cudaStream_t st);
+
+}  // namespace clk

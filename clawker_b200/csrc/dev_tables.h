@@ -1,0 +1,118 @@
+// dev_tables.h — immutable device snapshot of the firewall tables (host builds, kernels read).
+//
+// Layouts mirror the reference's BPF maps (internal/ebpf/bpf/common.h:80-177) flattened into
+// open-addressing tables whose slots are single 8/16-byte words so that one 64-/128-bit load
+// answers a lookup.  Everything here is POD and shared verbatim between engine.cpp (host) and
+// classify.cu (device); hash functions are __host__ __device__ so both sides agree.
+#pragma once
+#include <stdint.h>
+#include "../../include/clawker_gpu.h"
+
+#if defined(__CUDACC__)
+#define CLK_HD __host__ __device__ __forceinline__
+#else
+#define CLK_HD inline
+#endif
+
+namespace clk {
+
+// ---- hashing --------------------------------------------------------------------------------
+CLK_HD uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+CLK_HD uint32_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (uint32_t)x;
+}
+
+// Polynomial name hash over lower-cased bytes, mod 2^64: H(s) = sum s[i] * B^(n-1-i).
+// Suffix hashes come out of one forward pass: H(s[k:]) = H(s) - H(s[:k]) * B^(n-k).
+// A hit is always confirmed by a byte compare against the stored name, so the hash only
+// has to be a good filter (collisions cost time, never correctness).
+static const uint64_t NAME_B    = 0x9E3779B97F4A7C15ull;          // odd
+static const uint64_t NAME_BINV = 0xF1DE83E19937733Dull;          // NAME_B * NAME_BINV == 1 (mod 2^64)
+CLK_HD uint64_t name_key(uint64_t suffix_hash, uint32_t len)
+{
+    uint64_t k = suffix_hash ^ ((uint64_t)len * 0xD6E8FEB86659FD93ull);
+    return k ? k : 1;                                              // 0 is the empty-slot marker
+}
+
+// ---- rows ------------------------------------------------------------------------------------
+#define CLK_ROW_ENFORCED 1u     // cgroup present in container_map (common.h:273)
+#define CLK_ROW_BYPASS   2u     // bypass_map[cg] == 1             (common.h:266-267)
+
+// One endpoint (packet source address -> socket identity + its container's config), 64 B.
+struct EpRow {
+    uint32_t ip;                // IPv4 key (0 for IPv6 endpoints)
+    uint32_t uid;
+    uint64_t cgroup_id;
+    uint32_t so_mark;
+    uint32_t flags;             // CLK_ROW_*
+    clk_container_config cfg;   // 28 B copy (valid when ENFORCED)
+    uint32_t crow;              // index of the cgroup's ContRow (metric key); 0xffffffff none
+    uint32_t ip6[2];            // low 8 bytes of an IPv6 key are in ip6x (see Ep6Key)
+};
+static_assert(sizeof(EpRow) == 64, "EpRow must be 64 B");
+
+// One cgroup (events API lookup + metric key -> cgroup_id), 48 B.
+struct ContRow {
+    uint64_t cgroup_id;
+    uint32_t flags;
+    clk_container_config cfg;
+    uint32_t _pad[2];
+};
+static_assert(sizeof(ContRow) == 48, "ContRow must be 48 B");
+
+struct Ep6Key { uint32_t a[4]; uint32_t row; uint32_t _pad[3]; };   // 32 B; row = index into EpRow
+static_assert(sizeof(Ep6Key) == 32, "Ep6Key");
+
+// Name table slot (zones and SNI server_names), 16 B: key==0 empty.
+struct NameSlot {
+    uint64_t key;               // name_key(hash, len)
+    uint32_t val;               // zones: DomainHash(zone) (types.go:121-125); SNI: entry index
+    uint32_t str_off;           // offset into names blob: [len u8][bytes]
+};
+
+// ---- dns_cache / route_map slots -------------------------------------------------------------
+// dns slot  : lo32 = ip (key), hi32 = domain_hash.             empty = ~0ull
+// route slot: [63:32] domain_hash, [31:16] dst_port, [15:0] envoy_port.   empty = ~0ull
+static const uint64_t SLOT_EMPTY = ~0ull;
+
+// ---- metrics (per-GPU metrics_map) -----------------------------------------------------------
+// Packed key: [31:0] domain_hash, [47:32] dst_port, [61:48] crow, [63:62] action+1 (never 0).
+CLK_HD uint64_t metric_pack(uint32_t hash, uint32_t port, uint32_t crow, uint32_t action)
+{
+    return (uint64_t)hash | ((uint64_t)(port & 0xffffu) << 32) | ((uint64_t)(crow & 0x3fffu) << 48) |
+           ((uint64_t)(action + 1) << 62);
+}
+#define CLK_MAX_CROWS 16384u
+
+// ---- the snapshot handed to kernels by value -------------------------------------------------
+struct DevTables {
+    const EpRow    *ep_rows;     uint32_t n_ep_rows;
+    const uint32_t *ep_slots;    uint32_t ep_mask;       // slot: EpRow index + 1 (0 empty), keyed by mix32(ip)
+    const Ep6Key   *ep6;         uint32_t n_ep6;         // linear (<= 256 rows), rarely non-empty
+    const ContRow  *crows;       uint32_t n_crows;
+    const uint32_t *cg_slots;    uint32_t cg_mask;       // slot: ContRow index + 1, keyed by mix64(cgroup_id)
+    const uint64_t *dns_slots;   uint32_t dns_mask;      // 0 mask + null => empty table
+    const uint64_t *route_slots; uint32_t route_mask;
+    uint32_t dns_ffff_present;   uint32_t dns_ffff_hash; // the one key/value pair that equals SLOT_EMPTY
+    // CIDR allow set (A12): 2 bits per /24 block: bit0 = covered by a prefix <= /24,
+    // bit1 = block has longer prefixes -> cidr_l2 (hash by block -> 256-bit host bitmap)
+    const uint32_t *cidr_l1;     uint32_t n_cidr;        // n_cidr == 0 => stage skipped
+    const uint32_t *cidr_l2_keys; const uint32_t *cidr_l2_bits; uint32_t cidr_l2_mask;   // key: block+1; bits: 8 words / slot
+    const NameSlot *zone_slots;  uint32_t zone_mask;
+    const NameSlot *sni_slots;   uint32_t sni_mask;
+    const uint8_t  *names;                               // blob for string confirmation
+    uint32_t coredns_ips[8];     uint32_t n_coredns;     // distinct cfg.coredns_ip values (DNS-answer stage)
+    // device metrics table
+    unsigned long long *m_keys;  unsigned long long *m_counts; uint32_t m_mask;
+    unsigned long long *m_dropped;
+    // sizes for optional shared-memory staging (bytes; 0 = do not stage)
+    uint32_t stage_dns_bytes, stage_route_bytes;
+};
+
+}  // namespace clk

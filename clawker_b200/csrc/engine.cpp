@@ -1,0 +1,849 @@
+// engine.cpp — host side of libclawker_gpu.so: BPF-map-shaped tables, snapshot publication,
+// batch classification entry points and counters.  Implements include/clawker_gpu.h.
+//
+// Threading model: every clk_map_* / clk_rules_* call takes the engine mutex and
+// edits the host shadow tables only.  clk_publish() flattens them into an immutable device
+// snapshot (double-buffered) — kernels receive the snapshot BY VALUE at launch, so a launch
+// always sees one complete epoch, exactly like a BPF program sees old-or-new map rows, never torn.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/clawker_gpu.h"
+#include "classify.h"
+#include "dev_tables.h"
+#include "rules.h"
+
+using namespace clk;
+
+namespace {
+
+thread_local std::string tl_error;
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Snapshot {
+    DevBuf ep_rows, ep_slots, ep6, crows, cg_slots, dns, route, cidr_l1, cidr_l2_keys, cidr_l2_bits, zone, sni, names;
+    void release() { for (DevBuf *b : { &ep_rows, &ep_slots, &ep6, &crows, &cg_slots, &dns, &route, &cidr_l1, &cidr_l2_keys, &cidr_l2_bits, &zone, &sni, &names }) b->release(); }
+};
+
+struct MetricKeyHash {
+    size_t operator()(const std::array<uint8_t, 16> &k) const { uint64_t a, b; memcpy(&a, k.data(), 8); memcpy(&b, k.data() + 8, 8); return (size_t)(mix64(a) ^ (uint64_t)mix64(b) << 32); }
+};
+
+uint32_t pow2_at_least(uint64_t n) { uint32_t c = 16; while (c < n) c <<= 1; return c; }
+
+}  // namespace
+
+struct clk_engine {
+    std::mutex mu;
+    std::string err;
+    bool host_only = false;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = { nullptr, nullptr, nullptr };
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t max_containers = 256, max_dns = 16384, max_routes = 8192, max_metrics = 16384, max_cidrs = 1u << 20;
+
+    // host shadow tables (the BPF maps)
+    std::unordered_map<uint64_t, clk_container_config> container;
+    std::unordered_map<uint64_t, uint8_t> bypass;
+    std::unordered_map<uint32_t, clk_dns_entry> dns;
+    std::unordered_map<uint64_t, uint16_t> route;                       // (hash << 16 | port) -> envoy_port
+    std::unordered_map<uint32_t, clk_endpoint> endpoint;
+    std::map<std::array<uint8_t, 16>, clk_endpoint> endpoint6;
+    std::map<std::pair<uint32_t, uint32_t>, uint8_t> cidr;              // (addr, mask)
+    CompiledRules compiled;                                              // zones / snis / mappings
+    bool dirty = true;
+
+    // stable cgroup -> ContRow index (metric keys reference it)
+    std::unordered_map<uint64_t, uint32_t> crow_of;
+    std::vector<uint64_t> crow_cg;
+
+    // device
+    Snapshot snap[2]; int active = 0; bool published = false;
+    DevTables T;                                                         // active snapshot
+    DevBuf m_keys, m_counts, m_dropped;
+    DevBuf work_pkts[3], work_offs[3], work_verd[3], scan_sums, scan_pos, scan_total, upd_out, ctr_block;
+    clk_stats stats;
+    int loader = LOADER_TMA_SW64;
+    bool stage_tables = true;
+    uint64_t chunk_pkts = 1u << 21;
+
+    clk_engine() { memset(&T, 0, sizeof T); memset(&stats, 0, sizeof stats); }
+};
+
+namespace {
+
+int fail(clk_engine *e, int code, const char *fmt, ...)
+{
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    tl_error = buf;
+    if (e) e->err = buf;
+    return code;
+}
+#define CUDA_TRY(e, call) do { cudaError_t _c = (call); if (_c != cudaSuccess) return fail((e), CLK_EIO, "%s: %s", #call, cudaGetErrorString(_c)); } while (0)
+#define NEED_GPU(e) do { if ((e)->host_only) return fail((e), CLK_ENOSYS, "engine was created host-only (no CUDA device): classification requires the GPU"); } while (0)
+
+struct MapSpec { size_t klen, vlen; };
+const MapSpec kSpecs[CLK_MAP__COUNT] = {
+    { 8, sizeof(clk_container_config) }, { 8, 1 }, { 4, sizeof(clk_dns_entry) }, { sizeof(clk_route_key), sizeof(clk_route_val) },
+    { sizeof(clk_metric_key), 8 }, { 4, sizeof(clk_endpoint) }, { 16, sizeof(clk_endpoint) }, { sizeof(clk_cidr), 1 },
+};
+
+uint64_t route_k(const clk_route_key *k) { return ((uint64_t)k->domain_hash << 16) | k->dst_port; }
+
+bool is_cidr_mask(uint32_t mask_nbo)
+{
+    uint32_t h = __builtin_bswap32(mask_nbo);
+    return ((~h) & ((~h) + 1)) == 0;          // ~h is 2^k - 1
+}
+int mask_plen(uint32_t mask_nbo) { return __builtin_popcount(mask_nbo); }
+
+uint64_t poly_hash(const std::string &s)
+{
+    uint64_t h = 0;
+    for (unsigned char c : s) { if (c >= 'A' && c <= 'Z') c = (unsigned char)(c + 32); h = h * NAME_B + c; }
+    return h;
+}
+
+// Build one name table (slots + blob entries appended to `blob`).
+void build_name_table(const std::vector<std::string> &names, const std::vector<uint32_t> &vals, std::vector<NameSlot> &slots,
+                      std::vector<uint8_t> &blob)
+{
+    uint32_t cap = pow2_at_least((uint64_t)names.size() * 2 + 1);
+    slots.assign(cap, NameSlot{ 0, 0, 0 });
+    for (size_t i = 0; i < names.size(); i++) {
+        const std::string &s = names[i];
+        if (s.size() > 255) continue;
+        uint32_t off = (uint32_t)blob.size();
+        blob.push_back((uint8_t)s.size());
+        for (unsigned char c : s) blob.push_back((c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c);
+        uint64_t key = name_key(poly_hash(s), (uint32_t)s.size());
+        uint32_t h = mix64(key) & (cap - 1);
+        while (slots[h].key) h = (h + 1) & (cap - 1);
+        slots[h] = NameSlot{ key, vals[i], off };
+    }
+}
+
+template <typename V> cudaError_t upload(DevBuf &b, const std::vector<V> &v, cudaStream_t st)
+{
+    if (v.empty()) return cudaSuccess;
+    cudaError_t e = b.ensure(v.size() * sizeof(V));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice, st);
+}
+
+uint32_t crow_index(clk_engine *e, uint64_t cg)
+{
+    auto it = e->crow_of.find(cg);
+    if (it != e->crow_of.end()) return it->second;
+    if (e->crow_cg.size() >= CLK_MAX_CROWS) return 0xffffffffu;
+    uint32_t idx = (uint32_t)e->crow_cg.size();
+    e->crow_cg.push_back(cg); e->crow_of[cg] = idx;
+    return idx;
+}
+
+int publish_locked(clk_engine *e)
+{
+    NEED_GPU(e);
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    CUDA_TRY(e, cudaDeviceSynchronize());              // no kernel may still read the buffers we are about to overwrite
+    Snapshot &S = e->snap[1 - e->active];
+    DevTables T; memset(&T, 0, sizeof T);
+    cudaStream_t st = e->stream;
+
+    // ---- cgroup rows (stable indices) -----------------------------------------------------------
+    for (auto &kv : e->container) if (crow_index(e, kv.first) == 0xffffffffu) return fail(e, CLK_E2BIG, "more than %u distinct cgroups", CLK_MAX_CROWS);
+    for (auto &kv : e->bypass)    if (crow_index(e, kv.first) == 0xffffffffu) return fail(e, CLK_E2BIG, "more than %u distinct cgroups", CLK_MAX_CROWS);
+    std::vector<ContRow> crows(e->crow_cg.size());
+    for (size_t i = 0; i < crows.size(); i++) {
+        ContRow &r = crows[i]; memset(&r, 0, sizeof r);
+        r.cgroup_id = e->crow_cg[i];
+        auto c = e->container.find(r.cgroup_id);
+        if (c != e->container.end()) { r.flags |= CLK_ROW_ENFORCED; r.cfg = c->second; }
+        auto b = e->bypass.find(r.cgroup_id);
+        if (b != e->bypass.end() && b->second == 1) r.flags |= CLK_ROW_BYPASS;
+    }
+    std::vector<uint32_t> cg_slots(pow2_at_least(crows.size() * 2 + 1), 0);
+    for (size_t i = 0; i < crows.size(); i++) {
+        uint32_t h = mix64(crows[i].cgroup_id) & (uint32_t)(cg_slots.size() - 1);
+        while (cg_slots[h]) h = (h + 1) & (uint32_t)(cg_slots.size() - 1);
+        cg_slots[h] = (uint32_t)i + 1;
+    }
+    // ---- endpoint rows ----------------------------------------------------------------------------
+    std::vector<EpRow> rows; std::vector<Ep6Key> ep6;
+    auto fill = [&](EpRow &r, const clk_endpoint &ep) {
+        r.uid = ep.uid; r.cgroup_id = ep.cgroup_id; r.so_mark = ep.so_mark; r.crow = 0xffffffffu;
+        auto it = e->crow_of.find(ep.cgroup_id);
+        if (it != e->crow_of.end()) { r.crow = it->second; r.flags = crows[it->second].flags; r.cfg = crows[it->second].cfg; }
+    };
+    for (auto &kv : e->endpoint) { EpRow r; memset(&r, 0, sizeof r); r.ip = kv.first; fill(r, kv.second); rows.push_back(r); }
+    std::vector<uint32_t> ep_slots(pow2_at_least(rows.size() * 2 + 1), 0);
+    for (size_t i = 0; i < rows.size(); i++) {
+        uint32_t h = mix32(rows[i].ip) & (uint32_t)(ep_slots.size() - 1);
+        while (ep_slots[h]) h = (h + 1) & (uint32_t)(ep_slots.size() - 1);
+        ep_slots[h] = (uint32_t)i + 1;
+    }
+    for (auto &kv : e->endpoint6) {
+        EpRow r; memset(&r, 0, sizeof r); fill(r, kv.second);
+        Ep6Key k; memset(&k, 0, sizeof k); memcpy(k.a, kv.first.data(), 16); k.row = (uint32_t)rows.size();
+        rows.push_back(r); ep6.push_back(k);
+    }
+    // ---- dns_cache / route_map --------------------------------------------------------------------
+    std::vector<uint64_t> dns_slots, route_slots;
+    if (!e->dns.empty()) {
+        dns_slots.assign(pow2_at_least(e->dns.size() * 2 + 1), SLOT_EMPTY);
+        uint32_t mask = (uint32_t)dns_slots.size() - 1;
+        for (auto &kv : e->dns) {
+            uint64_t s = (uint64_t)kv.first | ((uint64_t)kv.second.domain_hash << 32);
+            if (s == SLOT_EMPTY) { T.dns_ffff_present = 1; T.dns_ffff_hash = 0xffffffffu; continue; }
+            uint32_t h = mix32(kv.first) & mask;
+            while (dns_slots[h] != SLOT_EMPTY) h = (h + 1) & mask;
+            dns_slots[h] = s;
+        }
+    }
+    if (!e->route.empty()) {
+        route_slots.assign(pow2_at_least(e->route.size() * 2 + 1), SLOT_EMPTY);
+        uint32_t mask = (uint32_t)route_slots.size() - 1;
+        for (auto &kv : e->route) {
+            uint64_t s = (kv.first << 16) | kv.second;
+            uint32_t h = mix64(kv.first) & mask;
+            while (route_slots[h] != SLOT_EMPTY) h = (h + 1) & mask;
+            route_slots[h] = s;
+        }
+    }
+    // ---- CIDR directory (A12) ---------------------------------------------------------------------
+    std::vector<uint32_t> l1, l2_keys, l2_bits;
+    uint32_t n_cidr = 0;
+    if (!e->cidr.empty()) {
+        l1.assign((1u << 24) / 16, 0);
+        std::unordered_map<uint32_t, std::array<uint32_t, 8>> leaves;
+        for (auto &kv : e->cidr) {
+            uint32_t addr = kv.first.first, mask = kv.first.second;
+            if ((addr & mask) != addr) continue;           // is_in_subnet can never be true for it (common.h:220-223)
+            n_cidr++;
+            int plen = mask_plen(mask);
+            uint32_t base = __builtin_bswap32(addr);       // host-order network
+            if (plen <= 24) {
+                uint32_t b0 = base >> 8, cnt = 1u << (24 - plen);
+                for (uint32_t b = b0; b < b0 + cnt; b++) l1[b >> 4] |= 1u << ((b & 15) * 2);
+            } else {
+                uint32_t blk = base >> 8, h0 = base & 255u, cnt = 1u << (32 - plen);
+                l1[blk >> 4] |= 2u << ((blk & 15) * 2);
+                auto &leaf = leaves[blk];
+                for (uint32_t hst = h0; hst < h0 + cnt; hst++) leaf[hst >> 5] |= 1u << (hst & 31);
+            }
+        }
+        uint32_t cap = pow2_at_least(leaves.size() * 2 + 1);
+        l2_keys.assign(cap, 0); l2_bits.assign((size_t)cap * 8, 0);
+        for (auto &kv : leaves) {
+            uint32_t h = mix32(kv.first) & (cap - 1);
+            while (l2_keys[h]) h = (h + 1) & (cap - 1);
+            l2_keys[h] = kv.first + 1;
+            memcpy(&l2_bits[(size_t)h * 8], kv.second.data(), 32);
+        }
+        if (n_cidr == 0) { l1.clear(); l2_keys.clear(); l2_bits.clear(); }
+    }
+    // ---- name tables --------------------------------------------------------------------------------
+    std::vector<NameSlot> zone_slots, sni_slots; std::vector<uint8_t> blob;
+    if (!e->compiled.zones.empty()) {
+        std::vector<uint32_t> vals; for (auto &z : e->compiled.zones) vals.push_back(domain_hash(z.data(), z.size()));
+        build_name_table(e->compiled.zones, vals, zone_slots, blob);
+    }
+    if (!e->compiled.snis.empty()) {
+        std::vector<uint32_t> vals(e->compiled.snis.size()); for (size_t i = 0; i < vals.size(); i++) vals[i] = (uint32_t)i;
+        build_name_table(e->compiled.snis, vals, sni_slots, blob);
+    }
+    // ---- upload -------------------------------------------------------------------------------------
+    CUDA_TRY(e, upload(S.crows, crows, st));       CUDA_TRY(e, upload(S.cg_slots, cg_slots, st));
+    CUDA_TRY(e, upload(S.ep_rows, rows, st));      CUDA_TRY(e, upload(S.ep_slots, ep_slots, st));
+    CUDA_TRY(e, upload(S.ep6, ep6, st));
+    CUDA_TRY(e, upload(S.dns, dns_slots, st));     CUDA_TRY(e, upload(S.route, route_slots, st));
+    CUDA_TRY(e, upload(S.cidr_l1, l1, st));        CUDA_TRY(e, upload(S.cidr_l2_keys, l2_keys, st));
+    CUDA_TRY(e, upload(S.cidr_l2_bits, l2_bits, st));
+    CUDA_TRY(e, upload(S.zone, zone_slots, st));   CUDA_TRY(e, upload(S.sni, sni_slots, st));
+    CUDA_TRY(e, upload(S.names, blob, st));
+    CUDA_TRY(e, cudaStreamSynchronize(st));
+
+    T.ep_rows = rows.empty() ? nullptr : (const EpRow *)S.ep_rows.p; T.n_ep_rows = (uint32_t)e->endpoint.size();
+    T.ep_slots = (const uint32_t *)S.ep_slots.p; T.ep_mask = (uint32_t)ep_slots.size() - 1;
+    T.ep6 = ep6.empty() ? nullptr : (const Ep6Key *)S.ep6.p; T.n_ep6 = (uint32_t)ep6.size();
+    T.crows = crows.empty() ? nullptr : (const ContRow *)S.crows.p; T.n_crows = (uint32_t)crows.size();
+    T.cg_slots = (const uint32_t *)S.cg_slots.p; T.cg_mask = (uint32_t)cg_slots.size() - 1;
+    if (!dns_slots.empty()) { T.dns_slots = (const uint64_t *)S.dns.p; T.dns_mask = (uint32_t)dns_slots.size() - 1; }
+    if (!route_slots.empty()) { T.route_slots = (const uint64_t *)S.route.p; T.route_mask = (uint32_t)route_slots.size() - 1; }
+    T.n_cidr = n_cidr;
+    if (n_cidr) { T.cidr_l1 = (const uint32_t *)S.cidr_l1.p; T.cidr_l2_keys = (const uint32_t *)S.cidr_l2_keys.p; T.cidr_l2_bits = (const uint32_t *)S.cidr_l2_bits.p; T.cidr_l2_mask = (uint32_t)l2_keys.size() - 1; }
+    if (!zone_slots.empty()) { T.zone_slots = (const NameSlot *)S.zone.p; T.zone_mask = (uint32_t)zone_slots.size() - 1; }
+    if (!sni_slots.empty()) { T.sni_slots = (const NameSlot *)S.sni.p; T.sni_mask = (uint32_t)sni_slots.size() - 1; }
+    T.names = (const uint8_t *)S.names.p;
+    // distinct CoreDNS addresses (DNS-answer stage)
+    for (auto &kv : e->container) {
+        bool seen = false;
+        for (uint32_t i = 0; i < T.n_coredns; i++) seen |= T.coredns_ips[i] == kv.second.coredns_ip;
+        if (!seen && T.n_coredns < 8) T.coredns_ips[T.n_coredns++] = kv.second.coredns_ip;
+    }
+    std::sort(T.coredns_ips, T.coredns_ips + T.n_coredns);
+    T.m_keys = (unsigned long long *)e->m_keys.p; T.m_counts = (unsigned long long *)e->m_counts.p;
+    T.m_mask = e->T.m_mask; T.m_dropped = (unsigned long long *)e->m_dropped.p;
+    // shared-memory staging budget: dns <= 32 KiB, route <= 8 KiB
+    if (e->stage_tables) {
+        if (!dns_slots.empty() && dns_slots.size() * 8 <= 32768) T.stage_dns_bytes = (uint32_t)dns_slots.size() * 8;
+        if (!route_slots.empty() && route_slots.size() * 8 <= 8192) T.stage_route_bytes = (uint32_t)route_slots.size() * 8;
+    }
+    e->T = T; e->active = 1 - e->active; e->published = true; e->dirty = false;
+    return CLK_OK;
+}
+
+int ensure_published(clk_engine *e)
+{
+    if (!e->published || e->dirty) return publish_locked(e);
+    return CLK_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+uint32_t clk_abi_version(void) { return CLK_ABI_VERSION; }
+
+const char *clk_strerror(int code)
+{
+    switch (code) {
+    case CLK_OK: return "ok"; case CLK_ENOENT: return "key does not exist"; case CLK_EIO: return "CUDA error";
+    case CLK_E2BIG: return "map full"; case CLK_ENOMEM: return "out of memory"; case CLK_EEXIST: return "exists";
+    case CLK_EINVAL: return "invalid argument"; case CLK_ENOSYS: return "not available (host-only engine)";
+    default: return "unknown error";
+    }
+}
+
+const char *clk_last_error(const clk_engine *e) { return e ? e->err.c_str() : tl_error.c_str(); }
+
+int clk_engine_create(const clk_cfg *cfg, clk_engine **out)
+{
+    if (!out) return fail(nullptr, CLK_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (cfg && cfg->abi_version != CLK_ABI_VERSION) return fail(nullptr, CLK_EINVAL, "abi_version %u != %u", cfg->abi_version, CLK_ABI_VERSION);
+    clk_engine *e = new (std::nothrow) clk_engine();
+    if (!e) return fail(nullptr, CLK_ENOMEM, "out of memory");
+    if (cfg) {
+        if (cfg->max_containers) e->max_containers = cfg->max_containers;
+        if (cfg->max_dns_cache) e->max_dns = cfg->max_dns_cache;
+        if (cfg->max_routes) e->max_routes = cfg->max_routes;
+        if (cfg->max_metrics) e->max_metrics = cfg->max_metrics;
+        if (cfg->max_cidrs) e->max_cidrs = cfg->max_cidrs;
+        e->host_only = (cfg->flags & 1u) != 0;
+    }
+    if (const char *s = getenv("CLK_LOADER")) e->loader = atoi(s);
+    if (const char *s = getenv("CLK_STAGE")) e->stage_tables = atoi(s) != 0;
+    if (const char *s = getenv("CLK_CHUNK_PKTS")) { long v = atol(s); if (v >= 1024) e->chunk_pkts = (uint64_t)v; }
+    if (!e->host_only) {
+        int dev = cfg ? cfg->device : -1;
+        cudaError_t c;
+        if (dev < 0) { c = cudaGetDevice(&dev); if (c != cudaSuccess) { int r = fail(nullptr, CLK_EIO, "no CUDA device: %s", cudaGetErrorString(c)); delete e; return r; } }
+        e->device = dev;
+        int n_sm = 0;
+        if ((c = cudaSetDevice(dev)) != cudaSuccess || (c = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (c = cudaEventCreate(&e->ev0)) != cudaSuccess || (c = cudaEventCreate(&e->ev1)) != cudaSuccess ||
+            (c = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) {
+            int r = fail(nullptr, CLK_EIO, "CUDA init on device %d failed: %s", dev, cudaGetErrorString(c)); delete e; return r;
+        }
+        for (int i = 0; i < 3; i++) cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking);
+        e->stats.sm_count = (uint32_t)n_sm;
+        uint32_t slots = pow2_at_least((uint64_t)e->max_metrics * 2);
+        if (e->m_keys.ensure((size_t)slots * 8) != cudaSuccess || e->m_counts.ensure((size_t)slots * 8) != cudaSuccess || e->m_dropped.ensure(8) != cudaSuccess) {
+            int r = fail(nullptr, CLK_ENOMEM, "cudaMalloc metrics table (%u slots)", slots); delete e; return r;
+        }
+        cudaMemset(e->m_keys.p, 0, (size_t)slots * 8); cudaMemset(e->m_counts.p, 0, (size_t)slots * 8); cudaMemset(e->m_dropped.p, 0, 8);
+        e->T.m_mask = slots - 1;
+    }
+    *out = e;
+    return CLK_OK;
+}
+
+void clk_engine_destroy(clk_engine *e)
+{
+    if (!e) return;
+    if (!e->host_only) {
+        cudaSetDevice(e->device);
+        cudaDeviceSynchronize();
+        e->snap[0].release(); e->snap[1].release();
+        for (DevBuf *b : { &e->m_keys, &e->m_counts, &e->m_dropped, &e->scan_sums, &e->scan_pos, &e->scan_total, &e->upd_out, &e->ctr_block }) b->release();
+        for (int i = 0; i < 3; i++) { e->work_pkts[i].release(); e->work_offs[i].release(); e->work_verd[i].release(); if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]); }
+        if (e->ev0) cudaEventDestroy(e->ev0);
+        if (e->ev1) cudaEventDestroy(e->ev1);
+        if (e->stream) cudaStreamDestroy(e->stream);
+    }
+    delete e;
+}
+
+// ---- map ops ------------------------------------------------------------------------------------
+int clk_map_update(clk_engine *e, int id, const void *key, size_t klen, const void *val, size_t vlen)
+{
+    if (!e || !key || id < 0 || id >= CLK_MAP__COUNT) return fail(e, CLK_EINVAL, "bad map id %d", id);
+    if (id == CLK_MAP_METRICS) return fail(e, CLK_EINVAL, "metrics_map is written by the classifier only");
+    if (klen != kSpecs[id].klen || (id != CLK_MAP_CIDR && (vlen != kSpecs[id].vlen || !val))) return fail(e, CLK_EINVAL, "map %d: key/value size %zu/%zu, want %zu/%zu", id, klen, vlen, kSpecs[id].klen, kSpecs[id].vlen);
+    std::lock_guard<std::mutex> g(e->mu);
+    switch (id) {
+    case CLK_MAP_CONTAINER: { uint64_t k; memcpy(&k, key, 8); if (!e->container.count(k) && e->container.size() >= e->max_containers) return fail(e, CLK_E2BIG, "container_map full (%u)", e->max_containers); memcpy(&e->container[k], val, sizeof(clk_container_config)); break; }
+    case CLK_MAP_BYPASS: { uint64_t k; memcpy(&k, key, 8); if (!e->bypass.count(k) && e->bypass.size() >= e->max_containers) return fail(e, CLK_E2BIG, "bypass_map full"); e->bypass[k] = *(const uint8_t *)val; break; }
+    case CLK_MAP_DNS_CACHE: { uint32_t k; memcpy(&k, key, 4); if (!e->dns.count(k) && e->dns.size() >= e->max_dns) return fail(e, CLK_E2BIG, "dns_cache full (%u)", e->max_dns); memcpy(&e->dns[k], val, sizeof(clk_dns_entry)); break; }
+    case CLK_MAP_ROUTE: {
+        clk_route_key rk; memcpy(&rk, key, sizeof rk); clk_route_val rv; memcpy(&rv, val, sizeof rv);
+        uint64_t k = route_k(&rk);
+        if (((k << 16) | rv.envoy_port) == SLOT_EMPTY) return fail(e, CLK_EINVAL, "route {0xffffffff,65535}->65535 is not representable");
+        if (!e->route.count(k) && e->route.size() >= e->max_routes) return fail(e, CLK_E2BIG, "route_map full (%u)", e->max_routes);
+        e->route[k] = rv.envoy_port; break;
+    }
+    case CLK_MAP_ENDPOINT: { uint32_t k; memcpy(&k, key, 4); memcpy(&e->endpoint[k], val, sizeof(clk_endpoint)); break; }
+    case CLK_MAP_ENDPOINT6: { std::array<uint8_t, 16> k; memcpy(k.data(), key, 16); if (!e->endpoint6.count(k) && e->endpoint6.size() >= 256) return fail(e, CLK_E2BIG, "endpoint6 table full (256)"); memcpy(&e->endpoint6[k], val, sizeof(clk_endpoint)); break; }
+    case CLK_MAP_CIDR: {
+        clk_cidr c; memcpy(&c, key, sizeof c);
+        if (!is_cidr_mask(c.mask)) return fail(e, CLK_EINVAL, "mask %#x is not a CIDR prefix mask", c.mask);
+        if (!e->cidr.count({ c.addr, c.mask }) && e->cidr.size() >= e->max_cidrs) return fail(e, CLK_E2BIG, "cidr set full (%u)", e->max_cidrs);
+        e->cidr[{ c.addr, c.mask }] = 1; break;
+    }
+    }
+    e->dirty = true;
+    return CLK_OK;
+}
+
+int clk_map_delete(clk_engine *e, int id, const void *key, size_t klen)
+{
+    if (!e || !key || id < 0 || id >= CLK_MAP__COUNT || id == CLK_MAP_METRICS) return fail(e, CLK_EINVAL, "bad map id %d", id);
+    if (klen != kSpecs[id].klen) return fail(e, CLK_EINVAL, "map %d: key size %zu, want %zu", id, klen, kSpecs[id].klen);
+    std::lock_guard<std::mutex> g(e->mu);
+    size_t n = 0;
+    switch (id) {
+    case CLK_MAP_CONTAINER: { uint64_t k; memcpy(&k, key, 8); n = e->container.erase(k); break; }
+    case CLK_MAP_BYPASS:    { uint64_t k; memcpy(&k, key, 8); n = e->bypass.erase(k); break; }
+    case CLK_MAP_DNS_CACHE: { uint32_t k; memcpy(&k, key, 4); n = e->dns.erase(k); break; }
+    case CLK_MAP_ROUTE:     { clk_route_key rk; memcpy(&rk, key, sizeof rk); n = e->route.erase(route_k(&rk)); break; }
+    case CLK_MAP_ENDPOINT:  { uint32_t k; memcpy(&k, key, 4); n = e->endpoint.erase(k); break; }
+    case CLK_MAP_ENDPOINT6: { std::array<uint8_t, 16> k; memcpy(k.data(), key, 16); n = e->endpoint6.erase(k); break; }
+    case CLK_MAP_CIDR:      { clk_cidr c; memcpy(&c, key, sizeof c); n = e->cidr.erase({ c.addr, c.mask }); break; }
+    }
+    if (!n) return CLK_ENOENT;                          // ebpf.ErrKeyNotExist: callers treat as success (manager.go:222-231)
+    e->dirty = true;
+    return CLK_OK;
+}
+
+int clk_map_lookup(clk_engine *e, int id, const void *key, size_t klen, void *val, size_t vlen)
+{
+    if (!e || !key || !val || id < 0 || id >= CLK_MAP__COUNT || id == CLK_MAP_METRICS) return fail(e, CLK_EINVAL, "bad map id %d", id);
+    if (klen != kSpecs[id].klen || vlen != kSpecs[id].vlen) return fail(e, CLK_EINVAL, "map %d: key/value size", id);
+    std::lock_guard<std::mutex> g(e->mu);
+    switch (id) {
+    case CLK_MAP_CONTAINER: { uint64_t k; memcpy(&k, key, 8); auto it = e->container.find(k); if (it == e->container.end()) return CLK_ENOENT; memcpy(val, &it->second, vlen); return CLK_OK; }
+    case CLK_MAP_BYPASS:    { uint64_t k; memcpy(&k, key, 8); auto it = e->bypass.find(k); if (it == e->bypass.end()) return CLK_ENOENT; memcpy(val, &it->second, 1); return CLK_OK; }
+    case CLK_MAP_DNS_CACHE: { uint32_t k; memcpy(&k, key, 4); auto it = e->dns.find(k); if (it == e->dns.end()) return CLK_ENOENT; memcpy(val, &it->second, vlen); return CLK_OK; }
+    case CLK_MAP_ROUTE:     { clk_route_key rk; memcpy(&rk, key, sizeof rk); auto it = e->route.find(route_k(&rk)); if (it == e->route.end()) return CLK_ENOENT; clk_route_val rv = { it->second, 0 }; memcpy(val, &rv, vlen); return CLK_OK; }
+    case CLK_MAP_ENDPOINT:  { uint32_t k; memcpy(&k, key, 4); auto it = e->endpoint.find(k); if (it == e->endpoint.end()) return CLK_ENOENT; memcpy(val, &it->second, vlen); return CLK_OK; }
+    case CLK_MAP_ENDPOINT6: { std::array<uint8_t, 16> k; memcpy(k.data(), key, 16); auto it = e->endpoint6.find(k); if (it == e->endpoint6.end()) return CLK_ENOENT; memcpy(val, &it->second, vlen); return CLK_OK; }
+    case CLK_MAP_CIDR:      { clk_cidr c; memcpy(&c, key, sizeof c); auto it = e->cidr.find({ c.addr, c.mask }); if (it == e->cidr.end()) return CLK_ENOENT; *(uint8_t *)val = 1; return CLK_OK; }
+    }
+    return CLK_EINVAL;
+}
+
+int clk_map_count(clk_engine *e, int id, uint32_t *n)
+{
+    if (!e || !n || id < 0 || id >= CLK_MAP__COUNT) return fail(e, CLK_EINVAL, "bad map id %d", id);
+    std::lock_guard<std::mutex> g(e->mu);
+    switch (id) {
+    case CLK_MAP_CONTAINER: *n = (uint32_t)e->container.size(); break;
+    case CLK_MAP_BYPASS: *n = (uint32_t)e->bypass.size(); break;
+    case CLK_MAP_DNS_CACHE: *n = (uint32_t)e->dns.size(); break;
+    case CLK_MAP_ROUTE: *n = (uint32_t)e->route.size(); break;
+    case CLK_MAP_ENDPOINT: *n = (uint32_t)e->endpoint.size(); break;
+    case CLK_MAP_ENDPOINT6: *n = (uint32_t)e->endpoint6.size(); break;
+    case CLK_MAP_CIDR: *n = (uint32_t)e->cidr.size(); break;
+    default: return fail(e, CLK_EINVAL, "use clk_counters_read for metrics_map");
+    }
+    return CLK_OK;
+}
+
+int clk_map_iter(clk_engine *e, int id, void *keys, void *vals, uint32_t cap, uint32_t *n)
+{
+    if (!e || !n || id < 0 || id >= CLK_MAP__COUNT || id == CLK_MAP_METRICS) return fail(e, CLK_EINVAL, "bad map id %d", id);
+    std::lock_guard<std::mutex> g(e->mu);
+    uint8_t *kp = (uint8_t *)keys, *vp = (uint8_t *)vals; uint32_t i = 0;
+    auto put = [&](const void *k, const void *v) { if (i < cap) { if (kp) memcpy(kp + (size_t)i * kSpecs[id].klen, k, kSpecs[id].klen); if (vp) memcpy(vp + (size_t)i * kSpecs[id].vlen, v, kSpecs[id].vlen); } i++; };
+    switch (id) {
+    case CLK_MAP_CONTAINER: for (auto &kv : e->container) put(&kv.first, &kv.second); break;
+    case CLK_MAP_BYPASS:    for (auto &kv : e->bypass) put(&kv.first, &kv.second); break;
+    case CLK_MAP_DNS_CACHE: for (auto &kv : e->dns) put(&kv.first, &kv.second); break;
+    case CLK_MAP_ROUTE:     for (auto &kv : e->route) { clk_route_key rk = { (uint32_t)(kv.first >> 16), (uint16_t)(kv.first & 0xffff), 0 }; clk_route_val rv = { kv.second, 0 }; put(&rk, &rv); } break;
+    case CLK_MAP_ENDPOINT:  for (auto &kv : e->endpoint) put(&kv.first, &kv.second); break;
+    case CLK_MAP_ENDPOINT6: for (auto &kv : e->endpoint6) put(kv.first.data(), &kv.second); break;
+    case CLK_MAP_CIDR:      for (auto &kv : e->cidr) { clk_cidr c = { kv.first.first, kv.first.second }; put(&c, &kv.second); } break;
+    }
+    *n = i;
+    return CLK_OK;
+}
+
+int clk_routes_replace(clk_engine *e, const clk_route *routes, uint32_t n)
+{
+    if (!e || (n && !routes)) return fail(e, CLK_EINVAL, "routes is NULL");
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n > e->max_routes) return fail(e, CLK_E2BIG, "%u routes > max_entries %u", n, e->max_routes);
+    e->route.clear();
+    for (uint32_t i = 0; i < n; i++) e->route[((uint64_t)routes[i].domain_hash << 16) | routes[i].dst_port] = routes[i].envoy_port;   // later duplicates win (UpdateAny)
+    e->dirty = true;
+    return CLK_OK;
+}
+
+int clk_dns_update(clk_engine *e, uint32_t ip, uint32_t domain_hash_, uint32_t ttl, uint32_t now)
+{
+    if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
+    if (!now) now = (uint32_t)time(nullptr);
+    clk_dns_entry en = { domain_hash_, now + ttl };
+    return clk_map_update(e, CLK_MAP_DNS_CACHE, &ip, 4, &en, sizeof en);
+}
+
+int clk_dns_gc(clk_engine *e, uint32_t now)
+{
+    if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
+    if (!now) now = (uint32_t)time(nullptr);
+    std::lock_guard<std::mutex> g(e->mu);
+    int cleared = 0;
+    for (auto it = e->dns.begin(); it != e->dns.end();) {
+        if (it->second.expire_ts < now) { it = e->dns.erase(it); cleared++; } else ++it;       // manager.go:449-453
+    }
+    if (cleared) e->dirty = true;
+    return cleared;
+}
+
+// ---- rules ----------------------------------------------------------------------------------------
+int clk_validate_dst(const char *dst) { return (dst && validate_dst(dst)) ? CLK_OK : CLK_EINVAL; }
+uint32_t clk_domain_hash(const char *domain, size_t len) { return domain_hash(domain ? domain : "", domain ? len : 0); }
+int clk_ip_to_u32(const char *s, uint32_t *out) { uint32_t v = 0; bool ok = s && ip_to_u32(s, &v); if (out) *out = v; return ok ? CLK_OK : CLK_EINVAL; }
+int clk_cidr_to_addr_mask(const char *s, uint32_t *addr, uint32_t *mask)
+{
+    uint32_t a = 0, m = 0; bool ok = s && cidr_to_addr_mask(s, &a, &m);
+    if (addr) *addr = a; if (mask) *mask = m;
+    return ok ? CLK_OK : CLK_EINVAL;
+}
+
+int clk_rules_compile(clk_engine *e, const clk_rule *rules, uint32_t n, const clk_ports *ports, uint32_t *n_warnings)
+{
+    if (!e || (n && !rules)) return fail(e, CLK_EINVAL, "rules is NULL");
+    std::vector<EgressRule> rs(n);
+    for (uint32_t i = 0; i < n; i++) {
+        rs[i].dst = rules[i].dst ? rules[i].dst : ""; rs[i].proto = rules[i].proto ? rules[i].proto : "";
+        rs[i].action = rules[i].action ? rules[i].action : ""; rs[i].port = rules[i].port;
+    }
+    int base = ports && ports->tcp_port_base ? ports->tcp_port_base : 10001;
+    CompiledRules c = compile_rules(rs, base);
+    std::lock_guard<std::mutex> g(e->mu);
+    if (c.mappings.size() > e->max_routes) return fail(e, CLK_E2BIG, "%zu TCP mappings > route_map max_entries %u", c.mappings.size(), e->max_routes);
+    if (c.cidrs.size() > e->max_cidrs) return fail(e, CLK_E2BIG, "%zu CIDR rules > %u", c.cidrs.size(), e->max_cidrs);
+    e->route.clear();                                    // syncRoutes -> SyncRoutes: clear then Update each (manager.go:347-386)
+    for (auto &m : c.mappings) e->route[((uint64_t)domain_hash(m.dst.data(), m.dst.size()) << 16) | (uint16_t)m.dst_port] = (uint16_t)m.envoy_port;
+    e->cidr.clear();
+    for (auto &cm : c.cidrs) e->cidr[{ cm.first, cm.second }] = 1;
+    if (n_warnings) *n_warnings = c.warnings;
+    e->compiled = std::move(c);
+    e->dirty = true;
+    return CLK_OK;
+}
+
+int clk_rules_dump(clk_engine *e, int kind, char *buf, size_t cap)
+{
+    if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
+    std::lock_guard<std::mutex> g(e->mu);
+    std::string s;
+    if (kind == 0) for (auto &z : e->compiled.zones) s += z + "\n";
+    else if (kind == 1) for (auto &z : e->compiled.snis) s += z + "\n";
+    else if (kind == 2) for (auto &m : e->compiled.mappings) s += m.dst + ":" + std::to_string(m.dst_port) + ":" + std::to_string(m.envoy_port) + "\n";
+    else return fail(e, CLK_EINVAL, "kind %d", kind);
+    if (buf && cap) { size_t k = std::min(cap - 1, s.size()); memcpy(buf, s.data(), k); buf[k] = 0; }
+    return (int)s.size() + 1;
+}
+
+int clk_publish(clk_engine *e)
+{
+    if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
+    std::lock_guard<std::mutex> g(e->mu);
+    return publish_locked(e);
+}
+
+// ---- classification ---------------------------------------------------------------------------------
+static int finish_launch(clk_engine *e, const char *err, const LaunchInfo &li)
+{
+    if (err) return fail(e, CLK_EIO, "kernel launch failed: %s", err);
+    e->stats.kernel_launches++; e->stats.last_grid = li.grid; e->stats.last_block = li.block; e->stats.last_smem_bytes = li.smem;
+    return CLK_OK;
+}
+
+int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, uint64_t n, uint32_t flags, void *d_verdicts, void *stream)
+{
+    if (!e || (n && (!d_pkts || !d_verdicts))) return fail(e, CLK_EINVAL, "NULL buffer");
+    if (stride < 64 || stride % 16) return fail(e, CLK_EINVAL, "stride %u: must be >= 64 and a multiple of 16", stride);
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    LaunchInfo li = { 0, 0, 0 };
+    cudaEventRecord(e->ev0, st);
+    const char *err = launch_slots(e->T, d_pkts, stride, n, flags, (uint32_t *)d_verdicts, st, e->loader, &li);
+    cudaEventRecord(e->ev1, st);
+    return finish_launch(e, err, li);
+}
+
+int clk_classify_varlen_dev(clk_engine *e, const void *d_pkts, const void *d_offs16, uint64_t n, uint32_t flags, void *d_verdicts, void *stream)
+{
+    if (!e || (n && (!d_pkts || !d_verdicts || !d_offs16))) return fail(e, CLK_EINVAL, "NULL buffer");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    LaunchInfo li = { 0, 0, 0 };
+    cudaEventRecord(e->ev0, st);
+    const char *err = launch_varlen(e->T, d_pkts, (const uint32_t *)d_offs16, n, flags, (uint32_t *)d_verdicts, st, &li);
+    cudaEventRecord(e->ev1, st);
+    return finish_launch(e, err, li);
+}
+
+// Host-buffer entry: chunked 3-deep pipeline, each chunk = H2D copy -> kernel -> D2H copy on its own stream.
+static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, uint32_t stride, uint64_t n, uint32_t flags, uint32_t *verdicts)
+{
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    const uint64_t chunk = e->chunk_pkts;
+    uint64_t done = 0; int k = 0;
+    while (done < n) {
+        uint64_t cnt = std::min<uint64_t>(chunk, n - done);
+        if (offs16) {                                      // keep a chunk under 256 MiB of payload
+            const uint64_t cap16 = (256ull << 20) / 16;
+            while (cnt > 1 && (uint64_t)(offs16[done + cnt] - offs16[done]) > cap16) cnt /= 2;
+        }
+        int s = k % 3; cudaStream_t st = e->pipe[s];
+        CUDA_TRY(e, cudaStreamSynchronize(st));            // buffers of this lane are free again
+        LaunchInfo li = { 0, 0, 0 }; const char *err;
+        CUDA_TRY(e, e->work_verd[s].ensure(cnt * 4));
+        if (offs16) {
+            uint64_t b0 = (uint64_t)offs16[done] * 16, b1 = (uint64_t)offs16[done + cnt] * 16;
+            CUDA_TRY(e, e->work_pkts[s].ensure(b1 - b0 + 16));
+            CUDA_TRY(e, e->work_offs[s].ensure((cnt + 1) * 4));
+            CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(e, cudaMemcpyAsync(e->work_offs[s].p, offs16 + done, (cnt + 1) * 4, cudaMemcpyHostToDevice, st));
+            // offsets stay absolute: bias the base pointer instead of rewriting them
+            err = launch_varlen(e->T, (const uint8_t *)e->work_pkts[s].p - b0, (const uint32_t *)e->work_offs[s].p, cnt, flags, (uint32_t *)e->work_verd[s].p, st, &li);
+        } else {
+            CUDA_TRY(e, e->work_pkts[s].ensure(cnt * stride));
+            CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + done * stride, cnt * stride, cudaMemcpyHostToDevice, st));
+            err = launch_slots(e->T, e->work_pkts[s].p, stride, cnt, flags, (uint32_t *)e->work_verd[s].p, st, e->loader, &li);
+        }
+        rc = finish_launch(e, err, li); if (rc) return rc;
+        CUDA_TRY(e, cudaMemcpyAsync(verdicts + done, e->work_verd[s].p, cnt * 4, cudaMemcpyDeviceToHost, st));
+        done += cnt; k++;
+    }
+    for (int s = 0; s < 3; s++) CUDA_TRY(e, cudaStreamSynchronize(e->pipe[s]));
+    return CLK_OK;
+}
+
+int clk_classify_slots(clk_engine *e, const uint8_t *pkts, uint32_t stride, uint64_t n, uint32_t flags, uint32_t *verdicts)
+{
+    if (!e || (n && (!pkts || !verdicts))) return fail(e, CLK_EINVAL, "NULL buffer");
+    if (stride < 64 || stride % 16) return fail(e, CLK_EINVAL, "stride %u: must be >= 64 and a multiple of 16", stride);
+    return classify_host(e, pkts, nullptr, stride, n, flags, verdicts);
+}
+
+int clk_classify_varlen(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, uint64_t n, uint32_t flags, uint32_t *verdicts)
+{
+    if (!e || (n && (!pkts || !verdicts || !offs16))) return fail(e, CLK_EINVAL, "NULL buffer");
+    for (uint64_t i = 0; i < n; i++) if (offs16[i + 1] < offs16[i]) return fail(e, CLK_EINVAL, "offs16 not monotonic at %llu", (unsigned long long)i);
+    return classify_host(e, pkts, offs16, 0, n, flags, verdicts);
+}
+
+int clk_classify_events(clk_engine *e, const clk_event *events, uint64_t n, uint32_t flags, uint32_t *verdicts)
+{
+    if (!e || (n && (!events || !verdicts))) return fail(e, CLK_EINVAL, "NULL buffer");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    if (!n) return CLK_OK;
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    cudaStream_t st = e->pipe[0];
+    CUDA_TRY(e, e->work_pkts[0].ensure(n * sizeof(clk_event)));
+    CUDA_TRY(e, e->work_verd[0].ensure(n * 4));
+    CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[0].p, events, n * sizeof(clk_event), cudaMemcpyHostToDevice, st));
+    LaunchInfo li = { 0, 0, 0 };
+    const char *err = launch_events(e->T, (const clk_event *)e->work_pkts[0].p, n, flags, (uint32_t *)e->work_verd[0].p, st, &li);
+    rc = finish_launch(e, err, li); if (rc) return rc;
+    CUDA_TRY(e, cudaMemcpyAsync(verdicts, e->work_verd[0].p, n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(e, cudaStreamSynchronize(st));
+    return CLK_OK;
+}
+
+int clk_dns_answers(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, uint64_t n, const uint32_t *verdicts,
+                    clk_dns_update_rec *out, uint64_t cap, uint64_t *n_out, int apply, uint32_t now)
+{
+    if (!e || !n_out || (n && (!pkts || !offs16 || !verdicts))) return fail(e, CLK_EINVAL, "NULL buffer");
+    NEED_GPU(e);
+    *n_out = 0;
+    if (!n) return CLK_OK;
+    std::vector<clk_dns_update_rec> host_out;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        int rc = ensure_published(e); if (rc) return rc;
+        CUDA_TRY(e, cudaSetDevice(e->device));
+        cudaStream_t st = e->pipe[0];
+        uint64_t bytes = (uint64_t)offs16[n] * 16, total = 0;
+        for (uint64_t i = 0; i < n; i++) if (CLK_HOOK(verdicts[i]) == CLK_HOOK_NONE) total += CLK_NUPD(verdicts[i]);
+        uint32_t nb = (uint32_t)((n + 4095) / 4096);
+        CUDA_TRY(e, e->work_pkts[0].ensure(bytes + 16)); CUDA_TRY(e, e->work_offs[0].ensure((n + 1) * 4)); CUDA_TRY(e, e->work_verd[0].ensure(n * 4));
+        CUDA_TRY(e, e->scan_sums.ensure((size_t)nb * 8)); CUDA_TRY(e, e->scan_pos.ensure(n * 8)); CUDA_TRY(e, e->scan_total.ensure(8));
+        CUDA_TRY(e, e->upd_out.ensure((total + 1) * sizeof(clk_dns_update_rec)));
+        CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[0].p, pkts, bytes, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(e, cudaMemcpyAsync(e->work_offs[0].p, offs16, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(e, cudaMemcpyAsync(e->work_verd[0].p, verdicts, n * 4, cudaMemcpyHostToDevice, st));
+        const char *err = launch_dns_extract(e->T, e->work_pkts[0].p, (const uint32_t *)e->work_offs[0].p, n, (const uint32_t *)e->work_verd[0].p,
+                                             (unsigned long long *)e->scan_sums.p, (unsigned long long *)e->scan_pos.p, (unsigned long long *)e->scan_total.p,
+                                             (clk_dns_update_rec *)e->upd_out.p, total, st);
+        if (err) return fail(e, CLK_EIO, "dns extract launch failed: %s", err);
+        e->stats.kernel_launches += 4;
+        unsigned long long dev_total = 0;
+        CUDA_TRY(e, cudaMemcpyAsync(&dev_total, e->scan_total.p, 8, cudaMemcpyDeviceToHost, st));
+        host_out.resize(total);
+        if (total) CUDA_TRY(e, cudaMemcpyAsync(host_out.data(), e->upd_out.p, total * sizeof(clk_dns_update_rec), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(e, cudaStreamSynchronize(st));
+        if (dev_total != total) return fail(e, CLK_EIO, "dns extract: device total %llu != host total %llu", dev_total, (unsigned long long)total);
+    }
+    *n_out = host_out.size();
+    if (out) memcpy(out, host_out.data(), std::min<uint64_t>(cap, host_out.size()) * sizeof(clk_dns_update_rec));
+    if (apply) for (auto &u : host_out) { int rc = clk_dns_update(e, u.ip, u.domain_hash, u.ttl, now); if (rc && rc != CLK_E2BIG) return rc; }
+    return CLK_OK;
+}
+
+// ---- counters -----------------------------------------------------------------------------------------
+int clk_counters_block_rows(clk_engine *e, uint32_t *rows)
+{
+    if (!e || !rows) return fail(e, CLK_EINVAL, "NULL");
+    *rows = e->T.m_mask + 1;
+    return CLK_OK;
+}
+
+int clk_counters_export(clk_engine *e, void *d_block, void *stream)
+{
+    if (!e || !d_block) return fail(e, CLK_EINVAL, "NULL");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    const char *err = launch_counters_export(e->T, (clk_metric *)d_block, stream ? (cudaStream_t)stream : e->stream);
+    if (err) return fail(e, CLK_EIO, "counters export: %s", err);
+    e->stats.kernel_launches++;
+    return CLK_OK;
+}
+
+int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, void *stream)
+{
+    if (!e || !d_blocks) return fail(e, CLK_EINVAL, "NULL");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    const char *err = launch_counters_clear(e->T, st);
+    if (!err) err = launch_counters_import(e->T, (const clk_metric *)d_blocks, (unsigned long long)n_blocks * (e->T.m_mask + 1), st);
+    if (err) return fail(e, CLK_EIO, "counters import: %s", err);
+    e->stats.kernel_launches += 2;
+    return CLK_OK;
+}
+
+int clk_counters_read(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n)
+{
+    if (!e || !n) return fail(e, CLK_EINVAL, "NULL");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    uint32_t rows = e->T.m_mask + 1;
+    CUDA_TRY(e, e->ctr_block.ensure((size_t)rows * sizeof(clk_metric)));
+    const char *err = launch_counters_export(e->T, (clk_metric *)e->ctr_block.p, e->stream);
+    if (err) return fail(e, CLK_EIO, "counters export: %s", err);
+    e->stats.kernel_launches++;
+    std::vector<clk_metric> host(rows);
+    CUDA_TRY(e, cudaMemcpyAsync(host.data(), e->ctr_block.p, (size_t)rows * sizeof(clk_metric), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(&e->stats.metrics_dropped, e->m_dropped.p, 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    uint32_t k = 0;
+    for (auto &m : host) if (m.count) { if (out && k < cap) out[k] = m; k++; }
+    *n = k;
+    return CLK_OK;
+}
+
+int clk_counters_reset(clk_engine *e)
+{
+    if (!e) return fail(e, CLK_EINVAL, "NULL");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    const char *err = launch_counters_clear(e->T, e->stream);
+    if (err) return fail(e, CLK_EIO, "counters clear: %s", err);
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->stats.kernel_launches++;
+    return CLK_OK;
+}
+
+int clk_get_stats(clk_engine *e, clk_stats *out)
+{
+    if (!e || !out) return fail(e, CLK_EINVAL, "NULL");
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!e->host_only && e->stats.kernel_launches && e->ev0 && cudaEventQuery(e->ev1) == cudaSuccess) {
+        float ms = 0; if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->stats.last_kernel_ms = ms;
+    }
+    *out = e->stats;
+    return CLK_OK;
+}
+
+int clk_sync(clk_engine *e)
+{
+    if (!e) return fail(e, CLK_EINVAL, "NULL");
+    NEED_GPU(e);
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    return CLK_OK;
+}
+
+// Pinned host memory for packet ingest rings (true DMA for the host-buffer entry points).
+int clk_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(nullptr, CLK_EINVAL, "out is NULL");
+    cudaError_t c = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (c != cudaSuccess) return fail(nullptr, CLK_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(c));
+    return CLK_OK;
+}
+int clk_host_free(void *p) { if (p) cudaFreeHost(p); return CLK_OK; }
+
+}  // extern "C"

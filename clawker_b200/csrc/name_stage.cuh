@@ -1,0 +1,312 @@
+// name_stage.cuh — payload stages of the fused verdict (included by classify.cu, namespace clk).
+//
+//   DNS question  -> CoreDNS zone selection       (Corefile zones: internal/firewall/coredns.go:26-96;
+//                                                   matcher: coredns v1.14.2 core/dnsserver/server.go ServeDNS)
+//   TLS ClientHello -> SNI -> server_names match  (tables: internal/firewall/envoy.go:358-393,905-915;
+//                                                   matcher: Envoy v1.37 filter-chain server_names lookup)
+//   DNS answers   -> dns_cache update stream      (internal/dnsbpf/dnsbpf.go:75-97)
+//
+// Names are matched by a 64-bit polynomial suffix hash (one forward pass gives every label
+// suffix) against open-addressing tables, and every hash hit is confirmed byte-for-byte
+// against the stored name, so results equal an exact string-keyed map lookup.
+
+__device__ __forceinline__ uint32_t gb(const uint8_t *p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t gbe16(const uint8_t *p) { return (gb(p) << 8) | gb(p + 1); }
+__device__ __forceinline__ uint32_t lower(uint32_t c) { return (c - 'A' < 26u) ? c + 32u : c; }
+__device__ __forceinline__ bool zone_char(uint32_t c) { return (c - 'a' < 26u) || (c - '0' < 10u) || c == '_' || c == '-'; }
+
+// Second half of the IPv4 parse once ports are known (shared by the 64 B fast path and long-option packets).
+__device__ __forceinline__ void finish_long_options(const DevTables &T, const uint8_t *pk, uint32_t avail, uint32_t flags, Parsed &p)
+{
+    uint32_t l4off = p.l4off, proto = p.proto, dst = p.ip, src = p.a0;
+    uint32_t sport = gbe16(pk + l4off), dport = gbe16(pk + l4off + 2);
+    p.hook = CLK_HOOK_NONE; p.ip = 0; p.a0 = 0;
+    const EpRow *row = ep_lookup4(T, src);
+    bool ingress = false;
+    if (!row && proto == 17) { row = ep_lookup4(T, dst); ingress = row != nullptr; }
+    if (!row) {
+        if (proto == 17 && sport == 53 && (flags & CLK_F_NAME_STAGE) && is_coredns(T, dst)) p.ans_candidate = true;
+        return;
+    }
+    p.row = row; p.ingress = ingress; p.ip = ingress ? src : dst;
+    if (proto == 6)       { p.hook = CLK_HOOK_CONNECT4; p.type = SOCK_STREAM_; p.port = dport; }
+    else if (proto == 17) { p.type = SOCK_DGRAM_; if (ingress) { p.hook = CLK_HOOK_RECVMSG4; p.port = sport; } else { p.hook = CLK_HOOK_SENDMSG4; p.port = dport; } }
+}
+
+// ---- DNS name walker (RFC 1035 §4.1.4; limits of miekg/dns UnpackDomainName: 255 octets, 126 pointers) -----
+struct NameWalk {
+    const uint8_t *m; uint32_t mlen, p, wire, after; int ptrs; bool jumped;
+    __device__ __forceinline__ void init(const uint8_t *m_, uint32_t mlen_, uint32_t off) { m = m_; mlen = mlen_; p = off; wire = 0; after = off; ptrs = 0; jumped = false; }
+    // Returns label length (>0) with p at its first byte, 0 at the root label, -1 if malformed.
+    __device__ __forceinline__ int next_label()
+    {
+        for (;;) {
+            if (p >= mlen) return -1;
+            uint32_t c = gb(m + p);
+            if ((c & 0xC0u) == 0xC0u) {
+                if (p + 1 >= mlen) return -1;
+                if (!jumped) { after = p + 2; jumped = true; }
+                if (++ptrs > 126) return -1;
+                p = ((c & 0x3Fu) << 8) | gb(m + p + 1);
+                continue;
+            }
+            if (c & 0xC0u) return -1;
+            if (c == 0) { if (!jumped) after = p + 1; return 0; }
+            if (p + 1 + c > mlen) return -1;
+            wire += c + 1; if (wire + 1 > 255) return -1;
+            p += 1;
+            return (int)c;
+        }
+    }
+};
+
+__device__ __forceinline__ bool name_table_find(const NameSlot *slots, uint32_t mask, uint64_t key, uint32_t &h, NameSlot &out)
+{
+    // continues probing from h; caller initialises h = mix64(key) & mask
+    for (;;) {
+        NameSlot s = slots[h];
+        h = (h + 1) & mask;
+        if (s.key == 0) return false;
+        if (s.key == key) { out = s; return true; }
+    }
+}
+
+// Confirm that the label sequence starting at wire offset `lab` (pointing at a length byte) spells `str`.
+__device__ __forceinline__ bool dns_name_equals(const uint8_t *m, uint32_t mlen, uint32_t lab, const uint8_t *str, uint32_t slen)
+{
+    NameWalk w; w.init(m, mlen, lab);
+    uint32_t k = 0; int c; bool first = true;
+    while ((c = w.next_label()) > 0) {
+        if (!first) { if (k >= slen || str[k] != '.') return false; k++; }
+        first = false;
+        for (int i = 0; i < c; i++) { if (k >= slen || str[k] != lower(gb(m + w.p + i))) return false; k++; }
+        w.p += c;
+    }
+    return c == 0 && k == slen;
+}
+
+// CoreDNS zone selection on the name at m[off..]: longest label suffix that is a configured zone.
+// Returns 1 (+ zone DomainHash) for a non-root zone, 0 for ".", -1 if the name is malformed.
+// *after = offset just past the name as stored.
+__device__ __forceinline__ int dns_zone_select(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t off, uint32_t *after, uint32_t *zone_hash)
+{
+    // pass 1: total hash H, text length n, B^n, last label holding a byte no zone can contain
+    NameWalk w; w.init(m, mlen, off);
+    uint64_t H = 0, Bn = 1; uint32_t n = 0; int labels = 0, last_bad = -1, c;
+    while ((c = w.next_label()) > 0) {
+        if (labels) { H = H * NAME_B + '.'; Bn *= NAME_B; n++; }
+        for (int i = 0; i < c; i++) {
+            uint32_t b = lower(gb(m + w.p + i));
+            if (!zone_char(b)) last_bad = labels;
+            H = H * NAME_B + b; Bn *= NAME_B; n++;
+        }
+        labels++; w.p += c;
+    }
+    if (c < 0) return -1;
+    *after = w.after;
+    if (T.zone_slots == nullptr) return 0;
+    // pass 2: prefix hash P and R = B^(n-k); suffix at label start k: H - P*R
+    w.init(m, mlen, off);
+    uint64_t P = 0, R = Bn; uint32_t k = 0; int lab = 0;
+    for (;;) {
+        uint32_t lab_off = w.p;                    // may be a pointer; next_label resolves it, so re-read below
+        c = w.next_label();
+        if (c <= 0) break;
+        lab_off = w.p - 1;
+        if (lab) { P = P * NAME_B + '.'; R *= NAME_BINV; k++; }
+        if (lab > last_bad) {
+            uint64_t key = name_key(H - P * R, n - k);
+            uint32_t h = mix64(key) & T.zone_mask; NameSlot s;
+            while (name_table_find(T.zone_slots, T.zone_mask, key, h, s)) {
+                const uint8_t *str = T.names + s.str_off;
+                if (str[0] == n - k && dns_name_equals(m, mlen, lab_off, str + 1, n - k)) { *zone_hash = s.val; return 1; }
+            }
+        }
+        for (int i = 0; i < c; i++) { P = P * NAME_B + lower(gb(m + w.p + i)); R *= NAME_BINV; k++; }
+        lab++; w.p += c;
+    }
+    return 0;
+}
+
+// DNS query arriving at CoreDNS (miekg/dns defaultMsgAcceptFunc, then ServeDNS zone routing).
+__device__ __forceinline__ uint32_t dns_query_verdict(const DevTables &T, const uint8_t *m, uint32_t mlen)
+{
+    if (mlen < 12) return CLK_N_DENY;
+    uint32_t fl = gbe16(m + 2);
+    if (fl & 0x8000u) return CLK_N_DENY;
+    uint32_t opcode = (fl >> 11) & 15u;
+    if (opcode != 0 && opcode != 4) return CLK_N_DENY;
+    if (gbe16(m + 4) != 1) return CLK_N_DENY;
+    if (gbe16(m + 6) > 1 || gbe16(m + 8) > 1 || gbe16(m + 10) > 2) return CLK_N_DENY;
+    uint32_t after, zh;
+    int z = dns_zone_select(T, m, mlen, 12, &after, &zh);
+    if (z < 0 || after + 4 > mlen) return CLK_N_DENY;
+    if (gbe16(m + after + 2) != 1) return CLK_N_DENY;
+    return z == 1 ? CLK_N_ALLOW : CLK_N_DENY;
+}
+
+__device__ __forceinline__ int dns_skip_name(const uint8_t *m, uint32_t mlen, uint32_t &p)
+{
+    uint32_t wire = 0;
+    for (;;) {
+        if (p >= mlen) return -1;
+        uint32_t c = gb(m + p);
+        if ((c & 0xC0u) == 0xC0u) { if (p + 1 >= mlen) return -1; p += 2; return 0; }
+        if (c & 0xC0u) return -1;
+        if (c == 0) { p += 1; return 0; }
+        wire += c + 1; if (wire + 1 > 255) return -1;
+        p += 1 + c;
+    }
+}
+
+// dnsbpf.Handler.writeARecords over the wire form.  out == nullptr: count only.
+__device__ __forceinline__ uint32_t dns_answer_updates(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t pkt_index,
+                                                       clk_dns_update_rec *out, unsigned long long pos, unsigned long long cap, uint32_t *name_v)
+{
+    *name_v = CLK_N_DENY;
+    if (mlen < 12) return 0;
+    uint32_t fl = gbe16(m + 2);
+    if (!(fl & 0x8000u)) return 0;
+    if (gbe16(m + 4) != 1) return 0;
+    uint32_t an = gbe16(m + 6), rest = gbe16(m + 8) + gbe16(m + 10);
+    uint32_t off, zone_hash;
+    int z = dns_zone_select(T, m, mlen, 12, &off, &zone_hash);
+    if (z < 0 || off + 4 > mlen) return 0;
+    off += 4;
+    if (z != 1) return 0;
+    *name_v = CLK_N_ALLOW;
+    uint32_t p = off;
+    for (uint32_t i = 0; i < an + rest; i++) {                      // framing pass: any malformed RR voids the message
+        if (dns_skip_name(m, mlen, p)) return 0;
+        if (p + 10 > mlen) return 0;
+        uint32_t type = gbe16(m + p), rdlen = gbe16(m + p + 8);
+        if (p + 10 + rdlen > mlen) return 0;
+        if (i < an && type == 1 && rdlen != 4) return 0;
+        p += 10 + rdlen;
+    }
+    uint32_t nupd = 0; p = off;
+    for (uint32_t i = 0; i < an; i++) {
+        dns_skip_name(m, mlen, p);
+        uint32_t type = gbe16(m + p), rdlen = gbe16(m + p + 8);
+        if (type == 1) {
+            uint32_t ip = gb(m + p + 10) | (gb(m + p + 11) << 8) | (gb(m + p + 12) << 16) | (gb(m + p + 13) << 24);
+            if (ip != 0 && nupd < CLK_MAX_A_PER_PACKET) {
+                if (out && pos + nupd < cap) {
+                    uint32_t ttl = (gbe16(m + p + 4) << 16) | gbe16(m + p + 6);
+                    clk_dns_update_rec r; r.ip = ip; r.domain_hash = zone_hash; r.ttl = ttl ? ttl : 60u; r.packet = pkt_index;
+                    out[pos + nupd] = r;
+                }
+                nupd++;
+            }
+        }
+        p += 10 + rdlen;
+    }
+    return nupd;
+}
+
+__device__ __forceinline__ uint32_t dns_answer_word(const DevTables &T, const uint8_t *pk, const Parsed &p)
+{
+    uint32_t po = p.l4off + 8;
+    if (po > p.end) return 0;
+    uint32_t nv, n = dns_answer_updates(T, pk + po, p.end - po, 0, nullptr, 0, 0, &nv);
+    return (nv << 4) | (n << 27);
+}
+
+__device__ __forceinline__ void dns_answer_extract(const DevTables &T, const uint8_t *pk, uint32_t avail, uint32_t pkt_index,
+                                                   clk_dns_update_rec *out, unsigned long long pos, unsigned long long cap)
+{
+    // Only reached for packets the classify pass marked as IPv4/UDP answers; recompute the payload window.
+    uint32_t ihl = gb(pk + 14) & 15u, l4off = 14 + 4 * ihl;
+    uint32_t end = 14 + gbe16(pk + 16); if (end > avail) end = avail;
+    uint32_t po = l4off + 8, nv;
+    if (po > end) return;
+    dns_answer_updates(T, pk + po, end - po, pkt_index, out, pos, cap, &nv);
+}
+
+// ---- TLS ClientHello -> SNI -> Envoy server_names ----------------------------------------------------------
+__device__ __forceinline__ bool sni_equals(const uint8_t *host, uint32_t from, uint32_t n, const uint8_t *str)
+{
+    if (str[0] != n - from) return false;
+    for (uint32_t i = from; i < n; i++) if (str[1 + i - from] != lower(gb(host + i))) return false;
+    return true;
+}
+
+__device__ __forceinline__ bool sni_match(const DevTables &T, const uint8_t *host, uint32_t n)
+{
+    if (T.sni_slots == nullptr) return false;
+    uint64_t H = 0, Bn = 1;
+    for (uint32_t i = 0; i < n; i++) { H = H * NAME_B + lower(gb(host + i)); Bn *= NAME_B; }
+    uint64_t P = 0, R = Bn;
+    for (uint32_t pos = 0; pos < n; pos++) {
+        uint32_t c = lower(gb(host + pos));
+        // candidates: the whole name (pos 0), then every '.' at index >= 1 with pos < n - 1
+        if (pos == 0 || (c == '.' && pos + 1 < n)) {
+            uint64_t key = name_key(H - P * R, n - pos);
+            uint32_t h = mix64(key) & T.sni_mask; NameSlot s;
+            while (name_table_find(T.sni_slots, T.sni_mask, key, h, s))
+                if (sni_equals(host, pos, n, T.names + s.str_off)) return true;
+        }
+        P = P * NAME_B + c; R *= NAME_BINV;
+    }
+    return false;
+}
+
+__device__ __forceinline__ uint32_t tls_sni_verdict(const DevTables &T, const uint8_t *p, uint32_t n)
+{
+    if (n < 9 || gb(p) != 0x16u || gb(p + 1) != 0x03u) return CLK_N_DENY;
+    uint32_t rlen = gbe16(p + 3);
+    if (5 + rlen > n) return CLK_N_DENY;
+    const uint8_t *h = p + 5;
+    if (gb(h) != 1) return CLK_N_DENY;
+    uint32_t hl = (gb(h + 1) << 16) | (gb(h + 2) << 8) | gb(h + 3);
+    if (4 + hl > rlen) return CLK_N_DENY;
+    const uint8_t *b = h + 4;
+    if (hl < 35) return CLK_N_DENY;
+    uint32_t o = 34;
+    uint32_t sl = gb(b + o); o += 1 + sl; if (o + 2 > hl) return CLK_N_DENY;
+    uint32_t cl = gbe16(b + o); o += 2 + cl; if (o + 1 > hl) return CLK_N_DENY;
+    uint32_t ml = gb(b + o); o += 1 + ml; if (o + 2 > hl) return CLK_N_DENY;
+    uint32_t el = gbe16(b + o); o += 2; if (o + el != hl) return CLK_N_DENY;
+    const uint8_t *sni = nullptr; uint32_t snl = 0; bool seen = false;
+    while (o + 4 <= hl) {
+        uint32_t et = gbe16(b + o), xl = gbe16(b + o + 2); o += 4;
+        if (o + xl > hl) return CLK_N_DENY;
+        if (et == 0) {
+            if (seen) return CLK_N_DENY;
+            seen = true;
+            if (xl < 5) return CLK_N_DENY;
+            uint32_t ll = gbe16(b + o);
+            if (ll + 2 != xl || gb(b + o + 2) != 0) return CLK_N_DENY;
+            snl = gbe16(b + o + 3);
+            if (snl == 0 || snl > 255 || snl + 3 != ll) return CLK_N_DENY;
+            sni = b + o + 5;
+        }
+        o += xl;
+    }
+    if (o != hl || !sni) return CLK_N_DENY;
+    for (uint32_t i = 0; i < snl; i++) if (gb(sni + i) == 0) return CLK_N_DENY;
+    return sni_match(T, sni, snl) ? CLK_N_ALLOW : CLK_N_DENY;
+}
+
+// ---- gating: which payload stage applies to an egress packet ------------------------------
+__device__ __forceinline__ uint32_t name_stage(const DevTables &T, const uint8_t *pk, uint32_t avail, const Parsed &p, const Decision &d)
+{
+    if (p.ingress || d.verdict == CLK_V_DENY || !(p.proto == 6 || p.proto == 17)) return CLK_N_NA;
+    if (p.hook == CLK_HOOK_SOCK_CREATE || p.hook == CLK_HOOK_NONE) return CLK_N_NA;
+    const EpRow *r = p.row;
+    if (!(r->flags & CLK_ROW_ENFORCED)) return CLK_N_NA;                  // cgroup has no container_map row
+    if (p.v6 && !(p.a0 == 0 && p.a1 == 0 && p.a2 == 0xffff0000u)) return CLK_N_NA;
+    const clk_container_config *cfg = &r->cfg;
+    uint32_t fip = d.verdict == CLK_V_REWRITE ? d.new_ip : p.ip;
+    uint32_t fport = d.verdict == CLK_V_REWRITE ? d.new_port : p.port;
+    uint32_t po = 0, pl = 0;
+    if (p.proto == 17) { po = p.l4off + 8; if (po <= p.end) pl = p.end - po; }
+    else if (p.l4off + 13 <= avail) { uint32_t doff = (gb(pk + p.l4off + 12) >> 4) * 4; po = p.l4off + doff; if (doff >= 20 && po <= p.end) pl = p.end - po; }
+    if (fip == cfg->coredns_ip && fport == 53) {
+        if (p.proto == 17) return dns_query_verdict(T, pk + po, pl);
+        if (pl > 0) return (pl >= 2 && gbe16(pk + po) + 2 <= pl) ? dns_query_verdict(T, pk + po + 2, gbe16(pk + po)) : CLK_N_DENY;
+        return CLK_N_NA;
+    }
+    if (p.proto == 6 && fip == cfg->envoy_ip && fport == cfg->egress_port && pl > 0) return tls_sni_verdict(T, pk + po, pl);
+    return CLK_N_NA;
+}

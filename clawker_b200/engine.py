@@ -1,0 +1,328 @@
+"""ctypes binding of libclawker_gpu.so (include/clawker_gpu.h).
+
+The library is the product; this module only marshals numpy buffers into its C-ABI so the Python
+mirrors of the reference's Go packages (clawker_b200.ebpf / .dnsbpf / .firewall), the tests and
+bench.py can drive it.  There is no fallback: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from . import abi
+from .abi import (Cfg, ContainerConfig, DNSEntry, Endpoint, Cidr, Ports, Route, RouteKey, RouteVal, Rule, Stats,
+                  DNSUPD_DTYPE, EVENT_DTYPE, METRIC_DTYPE)
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libclawker_gpu.so"
+
+
+class ClkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"clk error {code}: {msg}")
+        self.code = code
+
+
+def build_library(force: bool = False) -> Path:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> clawker_b200/libclawker_gpu.so (in-tree)."""
+    srcs = list((PKG / "csrc").glob("*")) + [PKG.parent / "include" / "clawker_gpu.h"]
+    stale = not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs)
+    if force or stale:
+        r = subprocess.run(["make", "-C", str(PKG / "csrc")] + (["-B"] if force else []), capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building libclawker_gpu.so failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(the CUDA library is the product; there is no CPU fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    vp, u32, u64, i32, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_size_t
+    sig = {
+        "clk_abi_version": (u32, []),
+        "clk_strerror": (C.c_char_p, [i32]),
+        "clk_last_error": (C.c_char_p, [vp]),
+        "clk_engine_create": (i32, [C.POINTER(Cfg), C.POINTER(vp)]),
+        "clk_engine_destroy": (None, [vp]),
+        "clk_map_update": (i32, [vp, i32, vp, sz, vp, sz]),
+        "clk_map_delete": (i32, [vp, i32, vp, sz]),
+        "clk_map_lookup": (i32, [vp, i32, vp, sz, vp, sz]),
+        "clk_map_iter": (i32, [vp, i32, vp, vp, u32, C.POINTER(u32)]),
+        "clk_map_count": (i32, [vp, i32, C.POINTER(u32)]),
+        "clk_routes_replace": (i32, [vp, vp, u32]),
+        "clk_dns_update": (i32, [vp, u32, u32, u32, u32]),
+        "clk_dns_gc": (i32, [vp, u32]),
+        "clk_validate_dst": (i32, [C.c_char_p]),
+        "clk_domain_hash": (u32, [C.c_char_p, sz]),
+        "clk_ip_to_u32": (i32, [C.c_char_p, C.POINTER(u32)]),
+        "clk_cidr_to_addr_mask": (i32, [C.c_char_p, C.POINTER(u32), C.POINTER(u32)]),
+        "clk_rules_compile": (i32, [vp, vp, u32, C.POINTER(Ports), C.POINTER(u32)]),
+        "clk_rules_dump": (i32, [vp, i32, C.c_char_p, sz]),
+        "clk_publish": (i32, [vp]),
+        "clk_classify_slots": (i32, [vp, vp, u32, u64, u32, vp]),
+        "clk_classify_varlen": (i32, [vp, vp, vp, u64, u32, vp]),
+        "clk_classify_slots_dev": (i32, [vp, vp, u32, u64, u32, vp, vp]),
+        "clk_classify_varlen_dev": (i32, [vp, vp, vp, u64, u32, vp, vp]),
+        "clk_classify_events": (i32, [vp, vp, u64, u32, vp]),
+        "clk_dns_answers": (i32, [vp, vp, vp, u64, vp, vp, u64, C.POINTER(u64), i32, u32]),
+        "clk_counters_read": (i32, [vp, vp, u32, C.POINTER(u32)]),
+        "clk_counters_reset": (i32, [vp]),
+        "clk_counters_block_rows": (i32, [vp, C.POINTER(u32)]),
+        "clk_counters_export": (i32, [vp, vp, vp]),
+        "clk_counters_import": (i32, [vp, vp, u32, vp]),
+        "clk_get_stats": (i32, [vp, C.POINTER(Stats)]),
+        "clk_sync": (i32, [vp]),
+        "clk_host_alloc": (i32, [sz, C.POINTER(vp)]),
+        "clk_host_free": (i32, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTS = ["clk_abi_version", "clk_strerror", "clk_last_error", "clk_engine_create", "clk_engine_destroy",
+           "clk_map_update", "clk_map_delete", "clk_map_lookup", "clk_map_iter", "clk_map_count", "clk_routes_replace",
+           "clk_dns_update", "clk_dns_gc", "clk_validate_dst", "clk_domain_hash", "clk_ip_to_u32",
+           "clk_cidr_to_addr_mask", "clk_rules_compile", "clk_rules_dump", "clk_publish", "clk_classify_slots",
+           "clk_classify_varlen", "clk_classify_slots_dev", "clk_classify_varlen_dev", "clk_classify_events",
+           "clk_dns_answers", "clk_counters_read", "clk_counters_reset", "clk_counters_block_rows",
+           "clk_counters_export", "clk_counters_import", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
+
+
+def pinned_empty(nbytes: int) -> np.ndarray:
+    """uint8 array backed by clk_host_alloc (page-locked) memory; kept alive by the array's base."""
+    p = C.c_void_p()
+    rc = lib().clk_host_alloc(nbytes, C.byref(p))
+    if rc:
+        raise ClkError(rc, lib().clk_last_error(None).decode())
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().clk_host_free(self.ptr)
+            except Exception:
+                pass
+    _owners[arr.ctypes.data] = _Owner(p.value)
+    return arr
+
+
+_owners: dict = {}
+
+
+class Engine:
+    """One GPU's classifier instance (clk_engine)."""
+
+    def __init__(self, device: int = -1, host_only: bool = False, max_containers: int = 0, max_dns_cache: int = 0,
+                 max_routes: int = 0, max_metrics: int = 0, max_cidrs: int = 0):
+        self.L = lib()
+        cfg = Cfg(abi.OK + 1, device, max_containers, max_dns_cache, max_routes, max_metrics, max_cidrs, 1 if host_only else 0)
+        cfg.abi_version = self.L.clk_abi_version()
+        h = C.c_void_p()
+        rc = self.L.clk_engine_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise ClkError(rc, self.L.clk_last_error(None).decode())
+        self.h = h
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    def _ck(self, rc: int, ok=(0,)):
+        if rc not in ok:
+            raise ClkError(rc, self.L.clk_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.clk_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- map ops ------------------------------------------------------------------------------------
+    def map_update(self, map_id: int, key, val=None):
+        vp = C.byref(val) if val is not None else None
+        return self._ck(self.L.clk_map_update(self.h, map_id, C.byref(key), C.sizeof(key), vp, C.sizeof(val) if val is not None else 0))
+
+    def map_delete(self, map_id: int, key) -> int:
+        """Returns 0 or abi.ENOENT (ebpf.ErrKeyNotExist)."""
+        return self._ck(self.L.clk_map_delete(self.h, map_id, C.byref(key), C.sizeof(key)), ok=(0, abi.ENOENT))
+
+    def map_lookup(self, map_id: int, key, val):
+        rc = self._ck(self.L.clk_map_lookup(self.h, map_id, C.byref(key), C.sizeof(key), C.byref(val), C.sizeof(val)), ok=(0, abi.ENOENT))
+        return None if rc else val
+
+    def map_count(self, map_id: int) -> int:
+        n = C.c_uint32()
+        self._ck(self.L.clk_map_count(self.h, map_id, C.byref(n)))
+        return n.value
+
+    def routes_replace(self, routes):
+        arr = (Route * len(routes))(*[Route(*r) for r in routes])
+        self._ck(self.L.clk_routes_replace(self.h, arr, len(routes)))
+
+    def dns_update(self, ip: int, domain_hash: int, ttl: int, now: int = 0):
+        self._ck(self.L.clk_dns_update(self.h, ip, domain_hash, ttl, now))
+
+    def dns_gc(self, now: int = 0) -> int:
+        rc = self.L.clk_dns_gc(self.h, now)
+        if rc < 0:
+            self._ck(rc)
+        return rc
+
+    def load_tables(self, t: dict) -> "Engine":
+        """Load a neutral table set (clawker_b200.capture.base_tables form)."""
+        for cg, cfg in t.get("containers", {}).items():
+            self.map_update(abi.MAP_CONTAINER, C.c_uint64(cg), ContainerConfig(*cfg))
+        for cg, v in t.get("bypass", {}).items():
+            self.map_update(abi.MAP_BYPASS, C.c_uint64(cg), C.c_uint8(v))
+        for ip, (h, exp) in t.get("dns_cache", {}).items():
+            self.map_update(abi.MAP_DNS_CACHE, C.c_uint32(ip), DNSEntry(h, exp))
+        for (h, port), eport in t.get("routes", {}).items():
+            self.map_update(abi.MAP_ROUTE, RouteKey(h, port, 0), RouteVal(eport, 0))
+        for ip, (cg, uid, mark) in t.get("endpoints", {}).items():
+            self.map_update(abi.MAP_ENDPOINT, C.c_uint32(ip), Endpoint(cg, uid, mark))
+        for ip6, (cg, uid, mark) in t.get("endpoints6", {}).items():
+            self.map_update(abi.MAP_ENDPOINT6, (C.c_uint8 * 16)(*ip6), Endpoint(cg, uid, mark))
+        for addr, mask in t.get("cidrs", []):
+            self.map_update(abi.MAP_CIDR, Cidr(addr, mask), None)
+        return self
+
+    # ---- rules --------------------------------------------------------------------------------------
+    def compile_rules(self, rules, egress_port: int = 10000, tcp_port_base: int = 10001) -> int:
+        """rules: iterable of dicts / objects with dst, proto, port, action.  Returns the warning count."""
+        def g(r, k, d):
+            return (r.get(k, d) if isinstance(r, dict) else getattr(r, k, d))
+        arr = (Rule * len(rules))()
+        keep = []
+        for i, r in enumerate(rules):
+            b = [str(g(r, "dst", "")).encode(), str(g(r, "proto", "") or "").encode(), str(g(r, "action", "") or "").encode()]
+            keep.append(b)
+            arr[i] = Rule(b[0], b[1], int(g(r, "port", 0) or 0), b[2])
+        w = C.c_uint32()
+        ports = Ports(egress_port, tcp_port_base)
+        self._ck(self.L.clk_rules_compile(self.h, arr, len(rules), C.byref(ports), C.byref(w)))
+        return w.value
+
+    def rules_dump(self, kind: int) -> list:
+        n = self.L.clk_rules_dump(self.h, kind, None, 0)
+        buf = C.create_string_buffer(n)
+        self.L.clk_rules_dump(self.h, kind, buf, n)
+        s = buf.value.decode()
+        return [x for x in s.split("\n") if x]
+
+    def publish(self):
+        self._ck(self.L.clk_publish(self.h))
+
+    # ---- classification -----------------------------------------------------------------------------
+    def classify_slots(self, pkts: np.ndarray, stride: int = 64, flags: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        pkts = np.ascontiguousarray(pkts, dtype=np.uint8)
+        n = pkts.size // stride
+        verd = out if out is not None else np.empty(n, dtype=np.uint32)
+        self._ck(self.L.clk_classify_slots(self.h, pkts.ctypes.data, stride, n, flags, verd.ctypes.data))
+        return verd
+
+    def classify_varlen(self, blob: np.ndarray, offs16: np.ndarray, flags: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        offs16 = np.ascontiguousarray(offs16, dtype=np.uint32)
+        n = offs16.size - 1
+        verd = out if out is not None else np.empty(n, dtype=np.uint32)
+        self._ck(self.L.clk_classify_varlen(self.h, blob.ctypes.data, offs16.ctypes.data, n, flags, verd.ctypes.data))
+        return verd
+
+    def classify_slots_dev(self, d_pkts: int, stride: int, n: int, flags: int, d_verdicts: int, stream: int = 0):
+        self._ck(self.L.clk_classify_slots_dev(self.h, d_pkts, stride, n, flags, d_verdicts, stream or None))
+
+    def classify_varlen_dev(self, d_pkts: int, d_offs16: int, n: int, flags: int, d_verdicts: int, stream: int = 0):
+        self._ck(self.L.clk_classify_varlen_dev(self.h, d_pkts, d_offs16, n, flags, d_verdicts, stream or None))
+
+    def classify_events(self, events: np.ndarray, flags: int = 0) -> np.ndarray:
+        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        verd = np.empty(events.size, dtype=np.uint32)
+        self._ck(self.L.clk_classify_events(self.h, events.ctypes.data, events.size, flags, verd.ctypes.data))
+        return verd
+
+    def dns_answers(self, blob: np.ndarray, offs16: np.ndarray, verdicts: np.ndarray, apply: bool = False, now: int = 0) -> np.ndarray:
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        offs16 = np.ascontiguousarray(offs16, dtype=np.uint32)
+        verdicts = np.ascontiguousarray(verdicts, dtype=np.uint32)
+        n = offs16.size - 1
+        cap = int(((verdicts >> 27) & 31)[((verdicts >> 24) & 7) == 0].sum())
+        out = np.zeros(cap, dtype=DNSUPD_DTYPE)
+        k = C.c_uint64()
+        self._ck(self.L.clk_dns_answers(self.h, blob.ctypes.data, offs16.ctypes.data, n, verdicts.ctypes.data,
+                                        out.ctypes.data, cap, C.byref(k), 1 if apply else 0, now))
+        return out[:k.value]
+
+    # ---- counters -----------------------------------------------------------------------------------
+    def counters(self) -> np.ndarray:
+        n = C.c_uint32()
+        self._ck(self.L.clk_counters_read(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=METRIC_DTYPE)
+        if n.value:
+            self._ck(self.L.clk_counters_read(self.h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def counters_reset(self):
+        self._ck(self.L.clk_counters_reset(self.h))
+
+    def counters_block_rows(self) -> int:
+        n = C.c_uint32()
+        self._ck(self.L.clk_counters_block_rows(self.h, C.byref(n)))
+        return n.value
+
+    def counters_export(self, d_block: int, stream: int = 0):
+        self._ck(self.L.clk_counters_export(self.h, d_block, stream or None))
+
+    def counters_import(self, d_blocks: int, n_blocks: int, stream: int = 0):
+        self._ck(self.L.clk_counters_import(self.h, d_blocks, n_blocks, stream or None))
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._ck(self.L.clk_get_stats(self.h, C.byref(s)))
+        return s
+
+    def sync(self):
+        self._ck(self.L.clk_sync(self.h))
+
+
+def domain_hash(s: str) -> int:
+    b = s.encode()
+    return lib().clk_domain_hash(b, len(b))
+
+
+def validate_dst(s: str) -> bool:
+    return lib().clk_validate_dst(s.encode()) == 0
+
+
+def ip_to_u32(s: str) -> int:
+    v = C.c_uint32()
+    lib().clk_ip_to_u32(s.encode(), C.byref(v))
+    return v.value
+
+
+def cidr_to_addr_mask(s: str):
+    a, m = C.c_uint32(), C.c_uint32()
+    if lib().clk_cidr_to_addr_mask(s.encode(), C.byref(a), C.byref(m)):
+        raise ValueError(s)
+    return a.value, m.value

@@ -1,0 +1,357 @@
+/*
+ * clawker_gpu.h — C-ABI of libclawker_gpu.so, the B200 batch egress classifier.
+ *
+ * This is the drop-in boundary for clawker's firewall verdict path.  Every entry
+ * point below names the reference interface it replaces (paths relative to the
+ * clawker repository root).  Plain pointers and sizes only: the intended caller
+ * is Go through cgo, so no C++/torch types appear here, no
+ * pointer is retained across calls, and no call aborts or throws — every export
+ * returns 0 or a negative CLK_E* code and leaves a message for clk_last_error().
+ *
+ * Byte order conventions are the reference's (internal/ebpf/types.go:86-111,
+ * internal/ebpf/bpf/common.h:80-113): IPv4 addresses are "network order bytes
+ * loaded as a native u32" (on little-endian a.b.c.d == a | b<<8 | c<<16 | d<<24),
+ * ports are host order.
+ */
+#ifndef CLAWKER_GPU_H
+#define CLAWKER_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLK_ABI_VERSION 1
+
+/* ---- error codes (negative errno style; ENOENT mirrors ebpf.ErrKeyNotExist,
+ *      internal/ebpf/manager.go:222-231) ------------------------------------ */
+#define CLK_OK        0
+#define CLK_ENOENT   (-2)   /* key not present (delete/lookup)                    */
+#define CLK_EIO      (-5)   /* CUDA runtime/driver failure, see clk_last_error()  */
+#define CLK_E2BIG    (-7)   /* map is at max_entries (BPF hash map full)          */
+#define CLK_ENOMEM   (-12)
+#define CLK_EEXIST   (-17)
+#define CLK_EINVAL   (-22)
+#define CLK_ENOSYS   (-38)
+
+/* ---- table row layouts: byte-identical to internal/ebpf/bpf/common.h -------- */
+
+/* struct container_config, common.h:80-89 / ebpf.ContainerConfig types.go:32-41 */
+typedef struct clk_container_config {
+    uint32_t envoy_ip;
+    uint32_t coredns_ip;
+    uint32_t gateway_ip;
+    uint32_t net_addr;
+    uint32_t net_mask;
+    uint32_t host_proxy_ip;
+    uint16_t host_proxy_port;
+    uint16_t egress_port;
+} clk_container_config;                 /* 28 B */
+
+/* struct dns_entry, common.h:96-99 */
+typedef struct clk_dns_entry {
+    uint32_t domain_hash;
+    uint32_t expire_ts;
+} clk_dns_entry;                        /* 8 B */
+
+/* struct route_key / route_val, common.h:103-113 */
+typedef struct clk_route_key {
+    uint32_t domain_hash;
+    uint16_t dst_port;
+    uint16_t _pad;
+} clk_route_key;                        /* 8 B */
+
+typedef struct clk_route_val {
+    uint16_t envoy_port;
+    uint16_t _pad;
+} clk_route_val;                        /* 4 B */
+
+/* struct metric_key, common.h:163-169; value is a u64 counter */
+typedef struct clk_metric_key {
+    uint64_t cgroup_id;
+    uint32_t domain_hash;
+    uint16_t dst_port;
+    uint8_t  action;                    /* CLK_ACTION_* */
+    uint8_t  _pad;
+} clk_metric_key;                       /* 16 B */
+
+typedef struct clk_metric {
+    clk_metric_key key;
+    uint64_t       count;
+} clk_metric;                           /* 24 B */
+
+/* ebpf.Route, internal/ebpf/manager.go:466-470 (JSON domain_hash,dst_port,envoy_port) */
+typedef struct clk_route {
+    uint32_t domain_hash;
+    uint16_t dst_port;
+    uint16_t envoy_port;
+} clk_route;
+
+#define CLK_ACTION_ALLOW  0             /* types.go:76-80 */
+#define CLK_ACTION_DENY   1
+#define CLK_ACTION_BYPASS 2
+
+/* ---- extension rows (no reference counterpart; SURVEY §8(d) packet→event) --- */
+
+/* Endpoint: binds a packet source address to the socket identity the cgroup
+ * hooks would have seen (bpf_get_current_cgroup_id / _uid_gid / SO_MARK,
+ * common.h:259-263,332-333).  Key: u32 IPv4 (CLK_MAP_ENDPOINT) or 16 B IPv6
+ * (CLK_MAP_ENDPOINT6). */
+typedef struct clk_endpoint {
+    uint64_t cgroup_id;
+    uint32_t uid;
+    uint32_t so_mark;
+} clk_endpoint;                         /* 16 B */
+
+/* IP/CIDR allow rule: same encoding as CIDRToAddrMask types.go:101-111 */
+typedef struct clk_cidr {
+    uint32_t addr;
+    uint32_t mask;
+} clk_cidr;
+
+/* ---- map ids for the generic BPF-map-like ops ------------------------------- */
+#define CLK_MAP_CONTAINER 0   /* u64 cgroup_id -> clk_container_config  (common.h:121-127) */
+#define CLK_MAP_BYPASS    1   /* u64 cgroup_id -> u8                    (common.h:131-137) */
+#define CLK_MAP_DNS_CACHE 2   /* u32 ip        -> clk_dns_entry         (common.h:141-147) */
+#define CLK_MAP_ROUTE     3   /* clk_route_key -> clk_route_val         (common.h:151-157) */
+#define CLK_MAP_METRICS   4   /* clk_metric_key-> u64 (read-only view)  (common.h:171-177) */
+#define CLK_MAP_ENDPOINT  5   /* u32 ip        -> clk_endpoint          (extension)        */
+#define CLK_MAP_ENDPOINT6 6   /* u8[16] ip6    -> clk_endpoint          (extension)        */
+#define CLK_MAP_CIDR      7   /* clk_cidr      -> u8 (set)              (extension, A12)   */
+#define CLK_MAP__COUNT    8
+
+/* ---- engine ------------------------------------------------------------------ */
+
+typedef struct clk_engine clk_engine;
+
+typedef struct clk_cfg {
+    uint32_t abi_version;        /* CLK_ABI_VERSION                                       */
+    int32_t  device;             /* CUDA ordinal; -1 = current                             */
+    /* max_entries; 0 = reference defaults 256/256/16384/8192/16384 (common.h:123-173)    */
+    uint32_t max_containers;
+    uint32_t max_dns_cache;
+    uint32_t max_routes;
+    uint32_t max_metrics;
+    uint32_t max_cidrs;          /* 0 = 1<<20                                              */
+    uint32_t flags;              /* CLK_CFG_*                                              */
+} clk_cfg;
+
+/* Host-only engine: tables, rule compiler and map ops work without a CUDA device (control-plane
+ * tests); every classification / publish / counters call fails with CLK_ENOSYS.  There is no
+ * CPU classification path in this library. */
+#define CLK_CFG_HOST_ONLY 1u
+
+/* Replaces ebpf.Manager.Load/OpenPinned (internal/ebpf/manager.go:41-133): creates the
+ * tables (host shadow + device snapshots) on one GPU. */
+int  clk_engine_create(const clk_cfg *cfg, clk_engine **out);
+void clk_engine_destroy(clk_engine *e);               /* Manager.Close manager.go:190-202 */
+const char *clk_last_error(const clk_engine *e);      /* thread-local when e == NULL        */
+const char *clk_strerror(int code);
+uint32_t clk_abi_version(void);
+
+/* BPF-map-shaped table ops.  Replace cilium/ebpf Map.Update/Delete/Lookup/Iterate as
+ * used in internal/ebpf/manager.go:249,325,347-386,390-414,443-463 and
+ * internal/dnsbpf/bpfmap.go:39-48.  Thread-safe.  Changes become visible to
+ * classification after clk_publish(). */
+int clk_map_update(clk_engine *e, int map_id, const void *key, size_t klen,
+                   const void *val, size_t vlen);
+int clk_map_delete(clk_engine *e, int map_id, const void *key, size_t klen);
+int clk_map_lookup(clk_engine *e, int map_id, const void *key, size_t klen,
+                   void *val, size_t vlen);
+/* Iterate: copies up to cap (key,value) rows; *n = total rows present. */
+int clk_map_iter(clk_engine *e, int map_id, void *keys, void *vals, uint32_t cap, uint32_t *n);
+int clk_map_count(clk_engine *e, int map_id, uint32_t *n);
+
+/* Manager.SyncRoutes (manager.go:347-386) as one atomic replace. */
+int clk_routes_replace(clk_engine *e, const clk_route *routes, uint32_t n);
+
+/* dnsbpf.MapWriter.Update / Manager.UpdateDNSCache (dnsbpf/bpfmap.go:39-48,
+ * ebpf/manager.go:408-414): dns_cache[ip] = {hash, now + ttl}.  `now` is passed in
+ * so tests are deterministic (0 = time(NULL)). */
+int clk_dns_update(clk_engine *e, uint32_t ip, uint32_t domain_hash, uint32_t ttl_seconds,
+                   uint32_t now);
+/* Manager.GarbageCollectDNS (manager.go:443-456): delete rows with expire_ts < now;
+ * returns number cleared (>= 0) or a negative error. */
+int clk_dns_gc(clk_engine *e, uint32_t now);
+
+/* ---- rule compiler (internal/firewall/{rules,coredns,envoy}.go) --- */
+
+/* config.EgressRule, internal/config/schema.go:131-138 (path rules are not on this path) */
+typedef struct clk_rule {
+    const char *dst;
+    const char *proto;           /* "" / NULL = default tls (rules.go:113-125)            */
+    int32_t     port;            /* 0 = default                                            */
+    const char *action;          /* "" / NULL = allow                                      */
+} clk_rule;
+
+typedef struct clk_ports {       /* firewall.EnvoyPorts envoy.go:12-16 */
+    int32_t egress_port;         /* 10000 consts.go:110 */
+    int32_t tcp_port_base;       /* 10001 consts.go:112 */
+} clk_ports;
+
+/* firewall.ValidateDst rules.go:33-107.  0 = valid, CLK_EINVAL otherwise. */
+int clk_validate_dst(const char *dst);
+/* ebpf.DomainHash types.go:121-125 (FNV-1a-32 of the ASCII-lowercased name). */
+uint32_t clk_domain_hash(const char *domain, size_t len);
+/* ebpf.IPToUint32 / CIDRToAddrMask types.go:86-111.  Return 0 / CLK_EINVAL. */
+int clk_ip_to_u32(const char *dotted, uint32_t *out);
+int clk_cidr_to_addr_mask(const char *cidr, uint32_t *addr, uint32_t *mask);
+
+/* normalizeAndDedup + GenerateCorefile zone set + serverNames + TCPMappings + syncRoutes
+ * (rules.go:138-161, coredns.go:26-96, envoy.go:54-83,905-915, manager.go:1356-1377).
+ * Replaces the engine's zone table, SNI table, CIDR set and route table from `rules`.
+ * n_warnings (may be NULL) receives the count of skipped rules (empty-domain etc.). */
+int clk_rules_compile(clk_engine *e, const clk_rule *rules, uint32_t n,
+                      const clk_ports *ports, uint32_t *n_warnings);
+/* Introspection of the compiled tables (for parity tests against the reference's
+ * golden vectors): newline-separated names in generation order. kind: 0 zones,
+ * 1 SNI server_names, 2 TCP mappings as "dst:port:envoy_port". Returns bytes needed. */
+int clk_rules_dump(clk_engine *e, int kind, char *buf, size_t cap);
+
+/* Epoch flip: builds the immutable device snapshot from the host tables
+ * (SURVEY §8(b) "Threading").  Classification always reads a complete snapshot. */
+int clk_publish(clk_engine *e);
+
+/* ---- classification ----------------------------------------------------------- */
+
+/* Verdict word:
+ *  [1:0]  route verdict   0 pass, 1 rewrite, 2 deny      (enum route_verdict common.h:292-296)
+ *  [3:2]  metric emitted  0 none, 1 ALLOW, 2 DENY, 3 BYPASS (metric_inc sites)
+ *  [5:4]  name verdict    0 n/a, 1 allow, 2 deny          (CoreDNS zone / Envoy SNI stage)
+ *  [7:6]  rewrite target  0 none, 1 coredns, 2 envoy egress, 3 envoy tcp listener
+ *  [23:8] rewritten port, host order (0 when not rewritten)
+ *  [26:24] hook           CLK_HOOK_*
+ *  [31:27] dns_cache updates this packet contributes (DNS answers, 0..31)           */
+#define CLK_V_PASS     0u
+#define CLK_V_REWRITE  1u
+#define CLK_V_DENY     2u
+#define CLK_M_NONE     0u
+#define CLK_M_ALLOW    1u
+#define CLK_M_DENY     2u
+#define CLK_M_BYPASS   3u
+#define CLK_N_NA       0u
+#define CLK_N_ALLOW    1u
+#define CLK_N_DENY     2u
+#define CLK_T_NONE     0u
+#define CLK_T_COREDNS  1u
+#define CLK_T_EGRESS   2u
+#define CLK_T_TCP      3u
+
+#define CLK_HOOK_NONE        0   /* non-IP, malformed, or no endpoint: no socket event */
+#define CLK_HOOK_CONNECT4    1   /* clawker.c:69  */
+#define CLK_HOOK_SENDMSG4    2   /* clawker.c:90  */
+#define CLK_HOOK_RECVMSG4    3   /* clawker.c:111 */
+#define CLK_HOOK_CONNECT6    4   /* clawker.c:134 */
+#define CLK_HOOK_SENDMSG6    5   /* clawker.c:167 */
+#define CLK_HOOK_RECVMSG6    6   /* clawker.c:198 */
+#define CLK_HOOK_SOCK_CREATE 7   /* clawker.c:224 */
+
+#define CLK_VERDICT(w)   ((w) & 3u)
+#define CLK_METRIC(w)    (((w) >> 2) & 3u)
+#define CLK_NAME(w)      (((w) >> 4) & 3u)
+#define CLK_TARGET(w)    (((w) >> 6) & 3u)
+#define CLK_PORT(w)      (((w) >> 8) & 0xffffu)
+#define CLK_HOOK(w)      (((w) >> 24) & 7u)
+#define CLK_NUPD(w)      (((w) >> 27) & 31u)
+
+#define CLK_MAX_A_PER_PACKET 31
+
+/* classify flags */
+#define CLK_F_NAME_STAGE  1u   /* run the DNS-zone / TLS-SNI / DNS-answer stages on payloads */
+#define CLK_F_NO_METRICS  2u   /* do not accumulate metrics_map (verdict bits [3:2] still set) */
+
+/* One socket event, the reference hooks' actual input (struct bpf_sock_addr fields
+ * used by clawker.c + the three bpf_get_current_* / getsockopt helper results). */
+typedef struct clk_event {
+    uint64_t cgroup_id;
+    uint32_t uid;
+    uint32_t so_mark;
+    uint32_t user_ip4;           /* NBO-in-native, used by the *4 hooks              */
+    uint32_t user_ip6[4];        /* used by the *6 hooks                             */
+    uint16_t user_port;          /* host order (reference holds it NBO in ctx)       */
+    uint8_t  hook;               /* CLK_HOOK_*                                       */
+    uint8_t  sock_type;          /* 1 STREAM, 2 DGRAM, 3 RAW                         */
+} clk_event;                     /* 40 B */
+
+/* A decoded dns_cache write, the argument triple of MapWriter.Update dnsbpf.go:32-34 */
+typedef struct clk_dns_update_rec {
+    uint32_t ip;
+    uint32_t domain_hash;
+    uint32_t ttl;                /* after the 0 -> 60 clamp dnsbpf.go:91-94 */
+    uint32_t packet;             /* index of the answer packet it came from */
+} clk_dns_update_rec;
+
+/* Packet batch layouts.
+ *  slot mode   : packet i is the `stride` bytes at pkts + i*stride (stride % 16 == 0, >= 64);
+ *  varlen mode : packet i is the bytes [16*offs16[i], 16*offs16[i+1]) of pkts
+ *                (every packet starts 16 B aligned; offs16 has n+1 entries).
+ * Frames are Ethernet II.  The *_dev variants take DEVICE pointers and only enqueue
+ * the kernel on `stream` (a cudaStream_t, NULL = the engine's stream); the host
+ * variants take HOST pointers, stage through pinned buffers, overlap H2D / kernel / D2H
+ * in chunks and return when `verdicts` is complete.
+ *
+ * Replaces: the kernel invoking clawker_connect4/sendmsg4/recvmsg4/connect6/sendmsg6/
+ * recvmsg6/sock_create per syscall (clawker.c:69-240) + CoreDNS zone selection +
+ * Envoy tls_inspector/server_names matching, fused per packet. */
+int clk_classify_slots(clk_engine *e, const uint8_t *pkts, uint32_t stride, uint64_t n,
+                       uint32_t flags, uint32_t *verdicts);
+int clk_classify_varlen(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, uint64_t n,
+                        uint32_t flags, uint32_t *verdicts);
+int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, uint64_t n,
+                           uint32_t flags, void *d_verdicts, void *stream);
+int clk_classify_varlen_dev(clk_engine *e, const void *d_pkts, const void *d_offs16, uint64_t n,
+                            uint32_t flags, void *d_verdicts, void *stream);
+
+/* Event-level entry: exactly the reference hooks' semantics on pre-parsed events
+ * (clawker.c:69-240 with common.h:256-451).  Host pointers. */
+int clk_classify_events(clk_engine *e, const clk_event *events, uint64_t n, uint32_t flags,
+                        uint32_t *verdicts);
+
+/* dnsbpf.Handler.writeARecords (dnsbpf.go:75-97) over the DNS-answer packets of a varlen
+ * batch already classified with CLK_F_NAME_STAGE: emits the MapWriter.Update triples in
+ * packet order, RR order.  Host pointers.  *n_out = records produced (<= cap written).
+ * apply != 0 additionally performs the updates (clk_dns_update with `now`). */
+int clk_dns_answers(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, uint64_t n,
+                    const uint32_t *verdicts, clk_dns_update_rec *out, uint64_t cap,
+                    uint64_t *n_out, int apply, uint32_t now);
+
+/* ---- counters (metrics_map, common.h:171-210) -------------------------------- */
+
+/* Sum view of the per-GPU counters: what summing the reference's PERCPU values gives.
+ * Copies up to cap rows; *n = rows present. */
+int clk_counters_read(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n);
+int clk_counters_reset(clk_engine *e);
+/* Fixed-size device block for the one collective of the multi-GPU path: the engine's
+ * metric table exported as `rows` x 24 B (clk_metric, count==0 rows are empty) into a
+ * caller-provided DEVICE buffer; after the caller's ncclAllGather of these blocks,
+ * clk_counters_import merges `n_blocks` gathered blocks (device pointer) into the local
+ * table, replacing it — every rank ends with the same summed view. */
+int clk_counters_block_rows(clk_engine *e, uint32_t *rows);
+int clk_counters_export(clk_engine *e, void *d_block, void *stream);
+int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, void *stream);
+
+/* ---- introspection for benches ------------------------------------------------ */
+typedef struct clk_stats {
+    uint64_t kernel_launches;    /* classification kernels launched so far            */
+    float    last_kernel_ms;     /* CUDA-event duration of the last classify kernel   */
+    uint32_t sm_count;
+    uint32_t last_grid;
+    uint32_t last_block;
+    uint32_t last_smem_bytes;
+    uint64_t metrics_dropped;    /* increments lost because the metric table was full */
+} clk_stats;
+int clk_get_stats(clk_engine *e, clk_stats *out);
+/* Block until the engine stream is idle. */
+int clk_sync(clk_engine *e);
+
+/* Pinned (page-locked) host memory for ingest rings: buffers from here are DMA'd directly by the
+ * host-buffer entry points; ordinary pageable memory also works, through the driver's staging. */
+int clk_host_alloc(size_t bytes, void **out);
+int clk_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLAWKER_GPU_H */
