@@ -5,12 +5,15 @@
 // against the device snapshot -> optional name stage (CoreDNS zone / TLS SNI / DNS answers)
 // -> one u32 verdict word, plus warp/CTA-aggregated metrics_map increments.
 //
-// Three ways to bring the 64 header bytes of a slot into registers, selected at launch:
-//   LOADER_TMA_SW64  2-D TMA tensor tiles (256 slots x 64 B, SWIZZLE_64B) through an mbarrier
-//                    ring; bank-conflict-free LDS.128 reads                       (default)
-//   LOADER_TMA       same without swizzle (debug)
-//   LOADER_DIRECT    four LDG.128 per thread straight from HBM (debug / odd strides)
-// The variable-length kernel (name stage) reads payloads through L1.
+// Kernels
+//   k_slots_fast   64-byte header slots.  2-D TMA tiles (256 slots x 64 B, SWIZZLE_64B) through an
+//                  mbarrier ring into shared memory; the common case (IPv4, no options, TCP/UDP/other)
+//                  runs as one branch-light predicated ladder with all 32 lanes converged; rare
+//                  packets (IPv6, IP options, non-IP, malformed) are compacted into a CTA queue and
+//                  classified together by the generic path.  Small tables (endpoints, dns_cache,
+//                  route_map) are staged into shared memory with 1-D TMA bulk copies.
+//   k_generic      any stride / varlen offsets, optional name stage; reads packets through L1.
+//   k_events       pre-parsed socket events (the reference hooks' own input).
 //
 // This is HBM-bound integer/byte work: no tensor cores anywhere on this path.
 #include <cuda_runtime.h>
@@ -61,13 +64,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
-{
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ void stg_stream(uint32_t *p, uint32_t v)
 {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -75,53 +71,72 @@ __device__ __forceinline__ void stg_stream(uint32_t *p, uint32_t v)
 __device__ __forceinline__ uint32_t bswap16(uint32_t v) { return __byte_perm(v, 0, 0x4401); }   // low 16 bits swapped
 
 // ------------------------------------------------------------------------------------------------
-// table lookups
+// per-CTA table views (shared-memory copies when staged, else the global arrays)
 // ------------------------------------------------------------------------------------------------
-struct Lk {                       // lookup views: point at the shared-memory copies when staged
-    const uint64_t *dns;   uint32_t dns_mask;
-    const uint64_t *route; uint32_t route_mask;
+struct Tabs {
+    const uint2    *ep;    uint32_t ep_mask, ep_shift;
+    const uint32_t *soa;   uint32_t soa_stride;
+    const uint4    *dns;   uint32_t dns_shift;
+    const uint4    *route; uint32_t route_shift;
+    const uint32_t *pre;                       // CIDR /16 prefilter (null when there are no CIDR rules)
 };
 
-__device__ __forceinline__ bool dns_lookup(const DevTables &T, const Lk &lk, uint32_t ip, uint32_t &hash)
+#define SOCK_STREAM_ 1u
+#define SOCK_DGRAM_  2u
+#define SOCK_RAW_    3u
+#define CLAWKER_MARK_ 0xC1A4u          // common.h:73
+#define DOCKER_DNS_NBO 0x0b00007fu     // bpf_htonl(0x7f00000b), common.h:62
+
+// dns_cache[ip] -> domain_hash.  One 16 B bucket load; second bucket only when the first is full.
+__device__ __forceinline__ bool dns_lookup(const DevTables &T, const Tabs &tb, uint32_t ip, uint32_t &hash)
 {
-    if (lk.dns) {
-        uint32_t h = mix32(ip) & lk.dns_mask;
-        #pragma unroll 1
-        for (;;) {
-            uint64_t s = lk.dns[h];
-            if (s == SLOT_EMPTY) break;
-            if ((uint32_t)s == ip) { hash = (uint32_t)(s >> 32); return true; }
-            h = (h + 1) & lk.dns_mask;
+    bool hit = false;
+    if (tb.dns) {
+        uint4 v = tb.dns[hash_a(ip) >> tb.dns_shift];
+        bool e0 = (v.x & v.y) == 0xffffffffu, e1 = (v.z & v.w) == 0xffffffffu;
+        if (v.x == ip && !e0) { hash = v.y; hit = true; }
+        else if (v.z == ip && !e1) { hash = v.w; hit = true; }
+        else if (!e0 && !e1) {
+            v = tb.dns[hash_b(ip) >> tb.dns_shift];
+            e0 = (v.x & v.y) == 0xffffffffu; e1 = (v.z & v.w) == 0xffffffffu;
+            if (v.x == ip && !e0) { hash = v.y; hit = true; }
+            else if (v.z == ip && !e1) { hash = v.w; hit = true; }
         }
     }
-    if (ip == 0xffffffffu && T.dns_ffff_present) { hash = T.dns_ffff_hash; return true; }
+    if (!hit && ip == 0xffffffffu && T.dns_ffff_present) { hash = T.dns_ffff_hash; hit = true; }
+    return hit;
+}
+
+// route_map[{hash, port}] -> envoy_port
+__device__ __forceinline__ bool route_lookup(const Tabs &tb, uint32_t hash, uint32_t port, uint32_t &eport)
+{
+    if (!tb.route) return false;
+    const uint32_t f = route_fold(hash, port), klo = port << 16;
+    uint4 v = tb.route[hash_a(f) >> tb.route_shift];
+    bool e0 = (v.x & v.y) == 0xffffffffu, e1 = (v.z & v.w) == 0xffffffffu;
+    // slot (lo, hi): hi = hash, lo = port << 16 | envoy_port
+    if (v.y == hash && (v.x & 0xffff0000u) == klo && !e0) { eport = v.x & 0xffffu; return true; }
+    if (v.w == hash && (v.z & 0xffff0000u) == klo && !e1) { eport = v.z & 0xffffu; return true; }
+    if (!e0 && !e1) {
+        v = tb.route[hash_b(f) >> tb.route_shift];
+        e0 = (v.x & v.y) == 0xffffffffu; e1 = (v.z & v.w) == 0xffffffffu;
+        if (v.y == hash && (v.x & 0xffff0000u) == klo && !e0) { eport = v.x & 0xffffu; return true; }
+        if (v.w == hash && (v.z & 0xffff0000u) == klo && !e1) { eport = v.z & 0xffffu; return true; }
+    }
     return false;
 }
 
-__device__ __forceinline__ bool route_lookup(const Lk &lk, uint32_t hash, uint32_t port, uint32_t &eport)
-{
-    if (!lk.route) return false;
-    uint64_t key = ((uint64_t)hash << 16) | port;
-    uint32_t h = mix64(key) & lk.route_mask;
-    #pragma unroll 1
-    for (;;) {
-        uint64_t s = lk.route[h];
-        if (s == SLOT_EMPTY) return false;
-        if ((s >> 16) == key) { eport = (uint32_t)(s & 0xffffu); return true; }
-        h = (h + 1) & lk.route_mask;
-    }
-}
-
 // A12: dst inside any allowed CIDR.  2-bit /24 directory + 256-bit leaf bitmaps, both L2-resident.
-__device__ __forceinline__ bool cidr_hit(const DevTables &T, uint32_t ip)
+__device__ __forceinline__ bool cidr_hit(const DevTables &T, const Tabs &tb, uint32_t ip)
 {
     if (T.n_cidr == 0) return false;
     uint32_t be = __byte_perm(ip, 0, 0x0123);          // host-order address
+    if (!((tb.pre[be >> 21] >> ((be >> 16) & 31u)) & 1u)) return false;       // no rule touches this /16
     uint32_t blk = be >> 8;
     uint32_t two = (__ldg(&T.cidr_l1[blk >> 4]) >> ((blk & 15u) * 2u)) & 3u;
     if (two & 1u) return true;
     if (two & 2u) {
-        uint32_t h = mix32(blk) & T.cidr_l2_mask;
+        uint32_t h = hash_a(blk) >> T.cidr_l2_shift;
         #pragma unroll 1
         for (;;) {
             uint32_t k = __ldg(&T.cidr_l2_keys[h]);
@@ -133,30 +148,30 @@ __device__ __forceinline__ bool cidr_hit(const DevTables &T, uint32_t ip)
     return false;
 }
 
-__device__ __forceinline__ const EpRow *ep_lookup4(const DevTables &T, uint32_t ip)
+// endpoint by IPv4 address -> EpRow index, or -1
+__device__ __forceinline__ int ep_find(const Tabs &tb, uint32_t ip)
 {
-    if (T.n_ep_rows == 0) return nullptr;
-    uint32_t h = mix32(ip) & T.ep_mask;
+    if (!tb.ep) return -1;
+    uint32_t h = hash_a(ip) >> tb.ep_shift;
     #pragma unroll 1
     for (;;) {
-        uint32_t s = __ldg(&T.ep_slots[h]);
-        if (s == 0) return nullptr;
-        const EpRow *r = &T.ep_rows[s - 1];
-        if (__ldg(&r->ip) == ip) return r;
-        h = (h + 1) & T.ep_mask;
+        uint2 s = tb.ep[h];
+        if (s.y == 0) return -1;
+        if (s.x == ip) return (int)s.y - 1;
+        h = (h + 1) & tb.ep_mask;
     }
 }
-__device__ __forceinline__ const EpRow *ep_lookup6(const DevTables &T, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3)
+__device__ __forceinline__ int ep_find6(const DevTables &T, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3)
 {
     for (uint32_t i = 0; i < T.n_ep6; i++) {
         const Ep6Key *k = &T.ep6[i];
-        if (k->a[0] == a0 && k->a[1] == a1 && k->a[2] == a2 && k->a[3] == a3) return &T.ep_rows[k->row];
+        if (k->a[0] == a0 && k->a[1] == a1 && k->a[2] == a2 && k->a[3] == a3) return (int)k->row;
     }
-    return nullptr;
+    return -1;
 }
 
 // ------------------------------------------------------------------------------------------------
-// decision ladder
+// decision ladder (generic form: used by the rare-packet path, the varlen kernel and the events kernel)
 // ------------------------------------------------------------------------------------------------
 struct Decision {
     uint32_t verdict, metric;     // CLK_V_*, CLK_M_*
@@ -164,26 +179,20 @@ struct Decision {
     uint32_t m_hash, m_port;      // metric key parts (valid when metric != 0)
 };
 
-#define SOCK_STREAM_ 1u
-#define SOCK_DGRAM_  2u
-#define SOCK_RAW_    3u
-#define CLAWKER_MARK_ 0xC1A4u          // common.h:73
-#define DOCKER_DNS_NBO 0x0b00007fu     // bpf_htonl(0x7f00000b), common.h:62
-
 __device__ __forceinline__ void emit(Decision &d, uint32_t hash, uint32_t port, uint32_t action)
 {
     d.metric = action + 1; d.m_hash = hash; d.m_port = port;
 }
 
 // decide_connect, common.h:323-410 (+ A12 at :350)
-__device__ __forceinline__ void decide_connect(const DevTables &T, const Lk &lk, const clk_container_config *cfg,
+__device__ __forceinline__ void decide_connect(const DevTables &T, const Tabs &tb, const clk_container_config *cfg,
                                                uint32_t mark, uint32_t type, uint32_t ip, uint32_t port, Decision &d)
 {
     if (mark == CLAWKER_MARK_) return;
     if (port == 53) { d.verdict = CLK_V_REWRITE; d.new_ip = cfg->coredns_ip; d.new_port = 53; emit(d, 0, 53, CLK_ACTION_ALLOW); return; }
     if ((ip & 0xffu) == 0x7fu) return;                                        // is_loopback :213-216
     if ((ip & cfg->net_mask) == cfg->net_addr) return;                        // is_in_subnet :220-223
-    if (cidr_hit(T, ip)) return;
+    if (cidr_hit(T, tb, ip)) return;
     uint32_t pp = cfg->host_proxy_port;
     if (cfg->host_proxy_ip != 0 && ip == cfg->host_proxy_ip && port == pp) return;
     if (ip == cfg->gateway_ip) {
@@ -193,8 +202,8 @@ __device__ __forceinline__ void decide_connect(const DevTables &T, const Lk &lk,
     }
     if (type == SOCK_DGRAM_) { emit(d, 0, port, CLK_ACTION_DENY); d.verdict = CLK_V_DENY; return; }
     uint32_t hash = 0, eport;
-    if (dns_lookup(T, lk, ip, hash)) {
-        if (route_lookup(lk, hash, port, eport)) {
+    if (dns_lookup(T, tb, ip, hash)) {
+        if (route_lookup(tb, hash, port, eport)) {
             d.verdict = CLK_V_REWRITE; d.new_ip = cfg->envoy_ip; d.new_port = eport;
             emit(d, hash, port, CLK_ACTION_ALLOW); return;
         }
@@ -204,18 +213,18 @@ __device__ __forceinline__ void decide_connect(const DevTables &T, const Lk &lk,
 }
 
 // decide_sendmsg, common.h:416-439 (+ A12)
-__device__ __forceinline__ void decide_sendmsg(const DevTables &T, const clk_container_config *cfg, uint32_t ip, uint32_t port, Decision &d)
+__device__ __forceinline__ void decide_sendmsg(const DevTables &T, const Tabs &tb, const clk_container_config *cfg, uint32_t ip, uint32_t port, Decision &d)
 {
     if (port == 53) { d.verdict = CLK_V_REWRITE; d.new_ip = cfg->coredns_ip; d.new_port = 53; return; }
     if ((ip & 0xffu) == 0x7fu) return;
     if ((ip & cfg->net_mask) == cfg->net_addr) return;
-    if (cidr_hit(T, ip)) return;
+    if (cidr_hit(T, tb, ip)) return;
     emit(d, 0, port, CLK_ACTION_DENY); d.verdict = CLK_V_DENY;
 }
 
 // The seven programs (clawker.c:69-240) behind enter_enforced (common.h:256-280).
 // ip = user_ip4 for *4 hooks, user_ip6[3] for *6 hooks; a0..a2 = user_ip6[0..2].
-__device__ __forceinline__ void run_hooks(const DevTables &T, const Lk &lk, uint32_t hook, uint32_t type, uint32_t uid,
+__device__ __forceinline__ void run_hooks(const DevTables &T, const Tabs &tb, uint32_t hook, uint32_t type, uint32_t uid,
                                           uint32_t mark, uint32_t flags, const clk_container_config *cfg,
                                           uint32_t ip, uint32_t port, uint32_t a0, uint32_t a1, uint32_t a2, Decision &d)
 {
@@ -226,8 +235,8 @@ __device__ __forceinline__ void run_hooks(const DevTables &T, const Lk &lk, uint
     if (!recv && (flags & CLK_ROW_BYPASS)) { emit(d, 0, 0, CLK_ACTION_BYPASS); return; }       // :265-271
     if (!(flags & CLK_ROW_ENFORCED)) return;                                                   // :273-275
     switch (hook) {
-    case CLK_HOOK_CONNECT4: decide_connect(T, lk, cfg, mark, type, ip, port, d); return;
-    case CLK_HOOK_SENDMSG4: decide_sendmsg(T, cfg, ip, port, d); return;
+    case CLK_HOOK_CONNECT4: decide_connect(T, tb, cfg, mark, type, ip, port, d); return;
+    case CLK_HOOK_SENDMSG4: decide_sendmsg(T, tb, cfg, ip, port, d); return;
     case CLK_HOOK_RECVMSG4:
         if (ip == cfg->coredns_ip && port == 53) { d.verdict = CLK_V_REWRITE; d.new_ip = DOCKER_DNS_NBO; d.new_port = 53; }
         return;
@@ -237,8 +246,8 @@ __device__ __forceinline__ void run_hooks(const DevTables &T, const Lk &lk, uint
         if (a0 == 0 && a1 == 0 && a2 == 0xffff0000u) {                                         // ::ffff:a.b.c.d
             if (hook == CLK_HOOK_CONNECT6) {
                 if (type != SOCK_STREAM_ && type != SOCK_DGRAM_) return;                       // clawker.c:146
-                decide_connect(T, lk, cfg, mark, type, ip, port, d);
-            } else decide_sendmsg(T, cfg, ip, port, d);
+                decide_connect(T, tb, cfg, mark, type, ip, port, d);
+            } else decide_sendmsg(T, tb, cfg, ip, port, d);
             return;
         }
         emit(d, 0, port, CLK_ACTION_DENY); d.verdict = CLK_V_DENY;                             // clawker.c:155,186
@@ -253,11 +262,11 @@ __device__ __forceinline__ void run_hooks(const DevTables &T, const Lk &lk, uint
     }
 }
 
-__device__ __forceinline__ uint32_t target_of(const clk_container_config *cfg, uint32_t ip, uint32_t port)
+__device__ __forceinline__ uint32_t target_of(uint32_t coredns_ip, uint32_t envoy_ip, uint32_t egress_port, uint32_t ip, uint32_t port)
 {
-    if (ip == cfg->coredns_ip && port == 53) return CLK_T_COREDNS;
-    if (ip == cfg->envoy_ip && port == cfg->egress_port) return CLK_T_EGRESS;
-    if (ip == cfg->envoy_ip) return CLK_T_TCP;
+    if (ip == coredns_ip && port == 53) return CLK_T_COREDNS;
+    if (ip == envoy_ip && port == egress_port) return CLK_T_EGRESS;
+    if (ip == envoy_ip) return CLK_T_TCP;
     return CLK_T_NONE;
 }
 
@@ -266,38 +275,51 @@ __device__ __forceinline__ uint32_t make_word(const Decision &d, const clk_conta
 {
     uint32_t w = d.verdict | (d.metric << 2) | (name << 4) | (hook << 24) | (nupd << 27);
     if (d.verdict == CLK_V_REWRITE) {
-        if (has_cfg) w |= target_of(cfg, d.new_ip, d.new_port) << 6;
+        if (has_cfg) w |= target_of(cfg->coredns_ip, cfg->envoy_ip, cfg->egress_port, d.new_ip, d.new_port) << 6;
         w |= (d.new_port & 0xffffu) << 8;
     }
     return w;
 }
 
 // ------------------------------------------------------------------------------------------------
-// metrics: warp match -> CTA shared-memory table -> device table (metric_inc common.h:190-210)
+// metrics: warp match -> CTA shared-memory table (hot keys) -> device table (metric_inc common.h:190-210)
 // ------------------------------------------------------------------------------------------------
-#define MSLOTS 1024u
+#define MSLOTS 512u
+
+__device__ __forceinline__ uint32_t mhash(unsigned long long key)
+{
+    return (uint32_t)(((key ^ (key >> 29)) * 0x9E3779B97F4A7C15ull) >> 32);
+}
 
 __device__ __forceinline__ void metric_global_add(const DevTables &T, unsigned long long key, unsigned long long cnt)
 {
-    uint32_t h = mix64(key) & T.m_mask;
+    uint32_t h = mhash(key) & T.m_mask;
     #pragma unroll 1
     for (int p = 0; p < 128; p++) {
-        unsigned long long old = atomicCAS(&T.m_keys[h], 0ull, key);
-        if (old == 0ull || old == key) { atomicAdd(&T.m_counts[h], cnt); return; }
-        h = (h + 1) & T.m_mask;
+        unsigned long long cur = T.m_keys[h];
+        if (cur != key) {
+            if (cur != 0ull) { h = (h + 1) & T.m_mask; continue; }
+            cur = atomicCAS(&T.m_keys[h], 0ull, key);
+            if (cur != 0ull && cur != key) { h = (h + 1) & T.m_mask; continue; }
+        }
+        atomicAdd(&T.m_counts[h], cnt);
+        return;
     }
     atomicAdd(T.m_dropped, cnt);       // table full: the reference's BPF_NOEXIST insert fails the same way
 }
 
 struct MetricAgg { unsigned long long *keys; unsigned int *counts; };
 
+// Two probes at most: keys that find a slot early (the frequent ones, by construction) stay in shared
+// memory for the CTA's lifetime; everything else goes straight to the device table.
 __device__ __forceinline__ void metric_cta_add(const DevTables &T, const MetricAgg &ag, unsigned long long key, unsigned int cnt)
 {
-    uint32_t h = mix64(key) & (MSLOTS - 1);
-    #pragma unroll 1
-    for (int p = 0; p < 8; p++) {
-        unsigned long long old = atomicCAS(&ag.keys[h], 0ull, key);
-        if (old == 0ull || old == key) { atomicAdd(&ag.counts[h], cnt); return; }
+    uint32_t h = mhash(key) & (MSLOTS - 1);
+    #pragma unroll
+    for (int p = 0; p < 2; p++) {
+        unsigned long long cur = ag.keys[h];
+        if (cur == 0ull) cur = atomicCAS(&ag.keys[h], 0ull, key);
+        if (cur == 0ull || cur == key) { atomicAdd(&ag.counts[h], cnt); return; }
         h = (h + 1) & (MSLOTS - 1);
     }
     metric_global_add(T, key, cnt);
@@ -321,7 +343,7 @@ __device__ __forceinline__ void metric_cta_flush(const DevTables &T, const Metri
 }
 
 // ------------------------------------------------------------------------------------------------
-// header parse: 64 bytes in four 16 B registers -> event
+// generic header parse: 64 bytes in four 16 B registers -> event
 // ------------------------------------------------------------------------------------------------
 struct Parsed {
     uint32_t hook, type, ip, port, a0, a1, a2;
@@ -343,9 +365,27 @@ __device__ __forceinline__ bool is_coredns(const DevTables &T, uint32_t ip)
     return false;
 }
 
-// avail = captured bytes of this packet (>= 64 whenever q0..q3 are fully valid; smaller for short frames)
-__device__ __forceinline__ void parse_headers(const DevTables &T, const uint4 &q0, const uint4 &q1, const uint4 &q2,
-                                              const uint4 &q3, uint32_t avail, uint32_t flags, Parsed &p)
+// Second half of the IPv4 parse once addresses and ports are known.
+__device__ __forceinline__ void finish_v4(const DevTables &T, const Tabs &tb, uint32_t flags, Parsed &p,
+                                          uint32_t src, uint32_t dst, uint32_t proto, uint32_t sport, uint32_t dport)
+{
+    int r = ep_find(tb, src);
+    bool ingress = false;
+    if (r < 0 && proto == 17) { r = ep_find(tb, dst); ingress = r >= 0; }
+    if (r < 0) {
+        if (proto == 17 && sport == 53 && (flags & CLK_F_NAME_STAGE) && is_coredns(T, dst)) p.ans_candidate = true;
+        return;
+    }
+    p.row = &T.ep_rows[r]; p.ingress = ingress; p.ip = ingress ? src : dst;
+    if (proto == 6)       { p.hook = CLK_HOOK_CONNECT4; p.type = SOCK_STREAM_; p.port = dport; }
+    else if (proto == 17) { p.type = SOCK_DGRAM_; if (ingress) { p.hook = CLK_HOOK_RECVMSG4; p.port = sport; } else { p.hook = CLK_HOOK_SENDMSG4; p.port = dport; } }
+    else                  { p.hook = CLK_HOOK_SOCK_CREATE; p.type = SOCK_RAW_; }
+}
+
+// pk: the packet in global memory (needed only when IPv4 options push the L4 ports past byte 64).
+// avail = captured bytes of this packet.
+__device__ __forceinline__ void parse_headers(const DevTables &T, const Tabs &tb, const uint4 &q0, const uint4 &q1, const uint4 &q2,
+                                              const uint4 &q3, const uint8_t *pk, uint32_t avail, uint32_t flags, Parsed &p)
 {
     p.hook = CLK_HOOK_NONE; p.type = 0; p.ip = 0; p.port = 0; p.a0 = p.a1 = p.a2 = 0;
     p.proto = 0; p.l4off = 0; p.end = 0; p.v6 = false; p.ingress = false; p.ans_candidate = false; p.row = nullptr;
@@ -368,20 +408,13 @@ __device__ __forceinline__ void parse_headers(const DevTables &T, const uint4 &q
             else if (l4off + 4 <= 64) {
                 sport = (hdr_byte(q0, q1, q2, q3, l4off) << 8) | hdr_byte(q0, q1, q2, q3, l4off + 1);
                 dport = (hdr_byte(q0, q1, q2, q3, l4off + 2) << 8) | hdr_byte(q0, q1, q2, q3, l4off + 3);
-            } else { p.l4off = l4off; p.proto = proto; p.end = end; p.ip = dst; p.a0 = src; p.hook = 0xffu; return; }   // ports beyond 64 B: caller finishes
+            } else {
+                sport = ((uint32_t)__ldg(pk + l4off) << 8) | __ldg(pk + l4off + 1);
+                dport = ((uint32_t)__ldg(pk + l4off + 2) << 8) | __ldg(pk + l4off + 3);
+            }
         }
-        const EpRow *row = ep_lookup4(T, src);
-        bool ingress = false;
-        if (!row && proto == 17) { row = ep_lookup4(T, dst); ingress = row != nullptr; }
         p.proto = proto; p.l4off = l4off; p.end = end;
-        if (!row) {
-            if (proto == 17 && sport == 53 && (flags & CLK_F_NAME_STAGE) && is_coredns(T, dst)) p.ans_candidate = true;
-            return;
-        }
-        p.row = row; p.ingress = ingress; p.ip = ingress ? src : dst;
-        if (proto == 6)       { p.hook = CLK_HOOK_CONNECT4; p.type = SOCK_STREAM_; p.port = dport; }
-        else if (proto == 17) { p.type = SOCK_DGRAM_; if (ingress) { p.hook = CLK_HOOK_RECVMSG4; p.port = sport; } else { p.hook = CLK_HOOK_SENDMSG4; p.port = dport; } }
-        else                  { p.hook = CLK_HOOK_SOCK_CREATE; p.type = SOCK_RAW_; }
+        finish_v4(T, tb, flags, p, src, dst, proto, sport, dport);
     } else if (et == 0x86DDu) {
         uint32_t vi = (q0.w >> 16) & 0xffu;
         if (avail < 54 || (vi >> 4) != 6) return;
@@ -395,12 +428,12 @@ __device__ __forceinline__ void parse_headers(const DevTables &T, const uint4 &q
                  s2 = __byte_perm(q1.w, q2.x, 0x5432), s3 = __byte_perm(q2.x, q2.y, 0x5432);
         uint32_t d0 = __byte_perm(q2.y, q2.z, 0x5432), d1 = __byte_perm(q2.z, q2.w, 0x5432),
                  d2 = __byte_perm(q2.w, q3.x, 0x5432), d3 = __byte_perm(q3.x, q3.y, 0x5432);
-        const EpRow *row = ep_lookup6(T, s0, s1, s2, s3);
+        int r = ep_find6(T, s0, s1, s2, s3);
         bool ingress = false;
-        if (!row && proto == 17) { row = ep_lookup6(T, d0, d1, d2, d3); ingress = row != nullptr; }
+        if (r < 0 && proto == 17) { r = ep_find6(T, d0, d1, d2, d3); ingress = r >= 0; }
         p.proto = proto; p.l4off = 54; p.end = end; p.v6 = true;
-        if (!row) return;
-        p.row = row; p.ingress = ingress;
+        if (r < 0) return;
+        p.row = &T.ep_rows[r]; p.ingress = ingress;
         if (ingress) { p.a0 = s0; p.a1 = s1; p.a2 = s2; p.ip = s3; } else { p.a0 = d0; p.a1 = d1; p.a2 = d2; p.ip = d3; }
         if (proto == 6)       { p.hook = CLK_HOOK_CONNECT6; p.type = SOCK_STREAM_; p.port = dport; }
         else if (proto == 17) { p.type = SOCK_DGRAM_; if (ingress) { p.hook = CLK_HOOK_RECVMSG6; p.port = sport; } else { p.hook = CLK_HOOK_SENDMSG6; p.port = dport; } }
@@ -410,115 +443,241 @@ __device__ __forceinline__ void parse_headers(const DevTables &T, const uint4 &q
 
 #include "name_stage.cuh"
 
-// Classify one parsed packet (no name stage) -> word + metric key.
-__device__ __forceinline__ uint32_t classify_parsed(const DevTables &T, const Lk &lk, const Parsed &p, Decision &d,
+// Classify one parsed packet (no name stage) -> decision + metric key.  Returns 0 when there is no event.
+__device__ __forceinline__ uint32_t classify_parsed(const DevTables &T, const Tabs &tb, const Parsed &p, Decision &d,
                                                     bool &has_metric, unsigned long long &mkey)
 {
     d.verdict = 0; d.metric = 0; d.new_ip = 0; d.new_port = 0; d.m_hash = 0; d.m_port = 0;
     has_metric = false; mkey = 0;
     if (p.hook == CLK_HOOK_NONE) return 0;
     const EpRow *r = p.row;
-    uint32_t flags = r->flags;
-    run_hooks(T, lk, p.hook, p.type, r->uid, r->so_mark, flags, &r->cfg, p.ip, p.port, p.a0, p.a1, p.a2, d);
+    run_hooks(T, tb, p.hook, p.type, r->uid, r->so_mark, r->flags, &r->cfg, p.ip, p.port, p.a0, p.a1, p.a2, d);
     if (d.verdict == CLK_V_REWRITE && d.new_ip == p.ip && d.new_port == p.port) d.verdict = CLK_V_PASS;   // identity rewrite
     if (d.metric) { has_metric = true; mkey = metric_pack(d.m_hash, d.m_port, r->crow, d.metric - 1); }
     return 1;
 }
 
+// One packet through the generic path (any layout; optional name stage).
+__device__ __noinline__ uint32_t generic_one(const DevTables &T, const Tabs &tb, const uint8_t *pk, uint32_t avail, uint32_t flags,
+                                             bool &hm, unsigned long long &mk)
+{
+    uint4 z = make_uint4(0, 0, 0, 0), q0 = z, q1 = z, q2 = z, q3 = z;
+    const uint4 *pq = (const uint4 *)pk;
+    if (avail >= 16) q0 = __ldg(pq);
+    if (avail >= 32) q1 = __ldg(pq + 1);
+    if (avail >= 48) q2 = __ldg(pq + 2);
+    if (avail >= 64) q3 = __ldg(pq + 3);
+    Parsed p; Decision d;
+    parse_headers(T, tb, q0, q1, q2, q3, pk, avail, flags, p);
+    if (p.ans_candidate) { hm = false; mk = 0; return dns_answer_word(T, pk, p); }
+    if (!classify_parsed(T, tb, p, d, hm, mk)) return 0;
+    uint32_t name = (flags & CLK_F_NAME_STAGE) ? name_stage(T, pk, avail, p, d) : CLK_N_NA;
+    return make_word(d, &p.row->cfg, (p.row->flags & CLK_ROW_ENFORCED) != 0, p.hook, name, 0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up common to the kernels
 // ------------------------------------------------------------------------------------------------
-struct SmemLayout { uint32_t agg_keys, agg_counts, dns, route, bars, tiles, total; };
+struct SmemLayout { uint32_t tiles, agg_keys, agg_counts, ep, soa, dns, route, pre, queue, bars, total; };
 
-__host__ __device__ inline SmemLayout smem_layout(uint32_t stage_dns, uint32_t stage_route, uint32_t tile_bytes, uint32_t stages)
+__host__ __device__ inline SmemLayout smem_layout(const DevTables &T, uint32_t tile_bytes, uint32_t queue_bytes, uint32_t n_bars)
 {
     SmemLayout L; uint32_t o = 0;
-    L.tiles = o; o += tile_bytes * stages;                 // 1024 B aligned tiles first (dynamic smem base is 1024 aligned by request)
+    L.tiles = o; o += tile_bytes;                          // 1024 B aligned tiles first
     L.agg_keys = o; o += MSLOTS * 8;
     L.agg_counts = o; o += MSLOTS * 4;
-    L.dns = o; o += (stage_dns + 15u) & ~15u;
-    L.route = o; o += (stage_route + 15u) & ~15u;
-    L.bars = o; o += 8 * 8;
+    L.ep = o; o += (T.stage_ep_bytes + 15u) & ~15u;
+    L.soa = o; o += (T.stage_soa_bytes + 15u) & ~15u;
+    L.dns = o; o += (T.stage_dns_bytes + 15u) & ~15u;
+    L.route = o; o += (T.stage_route_bytes + 15u) & ~15u;
+    L.pre = o; o += (T.stage_pre_bytes + 15u) & ~15u;
+    L.queue = o; o += queue_bytes;
+    L.bars = o; o += (n_bars + 1) * 8;
     L.total = o;
     return L;
 }
 
-// Stage dns/route slot arrays into shared memory with 1-D TMA bulk copies (thread 0), zero the
-// metric aggregation table, and return lookup views.  bars[7] is used for the table copy.
-__device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, const SmemLayout &L, Lk &lk, MetricAgg &ag)
+// Stage the small tables into shared memory with 1-D TMA bulk copies (thread 0), zero the metric
+// aggregation table, and return the table views.  bars[n_bars] is used for the table copy.
+__device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, const SmemLayout &L, uint32_t n_bars, Tabs &tb, MetricAgg &ag)
 {
     ag.keys = (unsigned long long *)(smem + L.agg_keys);
     ag.counts = (unsigned int *)(smem + L.agg_counts);
     for (uint32_t i = threadIdx.x; i < MSLOTS; i += blockDim.x) { ag.keys[i] = 0ull; ag.counts[i] = 0u; }
     uint64_t *bars = (uint64_t *)(smem + L.bars);
-    lk.dns = T.dns_slots; lk.dns_mask = T.dns_mask; lk.route = T.route_slots; lk.route_mask = T.route_mask;
-    uint32_t nb = T.stage_dns_bytes + T.stage_route_bytes;
-    if (threadIdx.x == 0) { for (int i = 0; i < 8; i++) mbar_init(&bars[i], 1); fence_mbar_init(); }
+    tb.ep = T.ep_slots; tb.ep_mask = T.ep_mask; tb.ep_shift = T.ep_shift; tb.soa = T.ep_soa; tb.soa_stride = T.soa_stride;
+    tb.dns = T.dns_b; tb.dns_shift = T.dns_shift; tb.route = T.route_b; tb.route_shift = T.route_shift; tb.pre = T.cidr_pre;
+    const uint32_t nb = T.stage_ep_bytes + T.stage_soa_bytes + T.stage_dns_bytes + T.stage_route_bytes + T.stage_pre_bytes;
+    if (threadIdx.x == 0) { for (uint32_t i = 0; i <= n_bars; i++) mbar_init(&bars[i], 1); fence_mbar_init(); }
     __syncthreads();
     if (nb) {
         if (threadIdx.x == 0) {
-            mbar_expect_tx(&bars[7], nb);
-            // bulk copies are limited to < 2^20 B each; staging budgets are far below that
-            if (T.stage_dns_bytes)   tma_load_1d(smem + L.dns, T.dns_slots, T.stage_dns_bytes, &bars[7]);
-            if (T.stage_route_bytes) tma_load_1d(smem + L.route, T.route_slots, T.stage_route_bytes, &bars[7]);
+            mbar_expect_tx(&bars[n_bars], nb);
+            if (T.stage_ep_bytes)    tma_load_1d(smem + L.ep, T.ep_slots, T.stage_ep_bytes, &bars[n_bars]);
+            if (T.stage_soa_bytes)   tma_load_1d(smem + L.soa, T.ep_soa, T.stage_soa_bytes, &bars[n_bars]);
+            if (T.stage_dns_bytes)   tma_load_1d(smem + L.dns, T.dns_b, T.stage_dns_bytes, &bars[n_bars]);
+            if (T.stage_route_bytes) tma_load_1d(smem + L.route, T.route_b, T.stage_route_bytes, &bars[n_bars]);
+            if (T.stage_pre_bytes)   tma_load_1d(smem + L.pre, T.cidr_pre, T.stage_pre_bytes, &bars[n_bars]);
         }
-        mbar_wait(&bars[7], 0);
-        if (T.stage_dns_bytes)   lk.dns = (const uint64_t *)(smem + L.dns);
-        if (T.stage_route_bytes) lk.route = (const uint64_t *)(smem + L.route);
+        mbar_wait(&bars[n_bars], 0);
+        if (T.stage_ep_bytes)    tb.ep = (const uint2 *)(smem + L.ep);
+        if (T.stage_soa_bytes)   tb.soa = (const uint32_t *)(smem + L.soa);
+        if (T.stage_dns_bytes)   tb.dns = (const uint4 *)(smem + L.dns);
+        if (T.stage_route_bytes) tb.route = (const uint4 *)(smem + L.route);
+        if (T.stage_pre_bytes)   tb.pre = (const uint32_t *)(smem + L.pre);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernel 1: 64-byte header slots through a TMA tile ring  (BASELINE configs 2, 4, 5)
 // ------------------------------------------------------------------------------------------------
-#define TILE_PKTS 256
-#define TILE_BYTES (TILE_PKTS * 64)
+#define FAST_WARPS 16           // warps per CTA
+#define WTILE_BYTES 2048        // one warp tile: 32 slots x 64 B
+#define WQ_CAP 64               // per-warp queue of rare packets (drained 32 at a time)
 
-template <int kStages, bool kSwizzle>
-__global__ void __launch_bounds__(TILE_PKTS) k_slots_tma(const __grid_constant__ DevTables T, const __grid_constant__ CUtensorMap map,
-                                                         const uint8_t *__restrict__ pkts, uint32_t stride,
-                                                         unsigned long long n, uint32_t flags, uint32_t *__restrict__ verdicts)
+// The common case as one predicated ladder.  Inputs: bytes 12..15 (w3), 16..31 (q1), 32..39 (q2x, q2y).
+// Returns false when the packet is not "simple IPv4" and must take the generic path.
+__device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb, uint32_t w3, const uint4 &q1, uint32_t q2x, uint32_t q2y,
+                                              uint32_t &word, bool &hm, unsigned long long &mk)
 {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemLayout L = smem_layout(T.stage_dns_bytes, T.stage_route_bytes, TILE_BYTES, kStages);
-    Lk lk; MetricAgg ag;
-    cta_prologue(T, smem, L, lk, ag);
-    uint64_t *bars = (uint64_t *)(smem + L.bars);
-    const uint32_t tid = threadIdx.x;
-    const unsigned long long n_tiles = (n + TILE_PKTS - 1) / TILE_PKTS;
-    const bool do_metrics = !(flags & CLK_F_NO_METRICS);
+    // Ethernet II + IPv4 without options, not a later fragment
+    if ((w3 & 0x00ffffffu) != 0x00450008u || (q1.y & 0xff1fu) != 0) return false;
+    const uint32_t proto = q1.y >> 24;
+    const uint32_t src = __byte_perm(q1.z, q1.w, 0x5432), dst = __byte_perm(q1.w, q2x, 0x5432);
+    const uint32_t sport = bswap16(q2x >> 16), dport = bswap16(q2y);
+    const bool tcp = proto == 6, udp = proto == 17, raw = !tcp && !udp;
 
-    // prologue: fill the ring
-    if (tid == 0) {
-        for (int s = 0; s < kStages; s++) {
-            unsigned long long t = blockIdx.x + (unsigned long long)s * gridDim.x;
-            if (t < n_tiles) { mbar_expect_tx(&bars[s], TILE_BYTES); tma_load_2d(smem + L.tiles + s * TILE_BYTES, &map, &bars[s], 0, (int)(t * TILE_PKTS)); }
+    int r = ep_find(tb, src);
+    bool ingress = false;
+    if (r < 0 && udp) { r = ep_find(tb, dst); ingress = r >= 0; }
+    word = 0; hm = false; mk = 0;
+    if (r < 0) return true;                                                      // no endpoint: no socket event
+
+    const uint32_t S = tb.soa_stride;
+    const uint32_t *so = tb.soa + r;
+    const uint32_t uid = so[SOA_UID * S], mark = so[SOA_MARK * S], fl = so[SOA_FLAGS * S];
+    const uint32_t envoy = so[SOA_ENVOY * S], coredns = so[SOA_COREDNS * S], gateway = so[SOA_GATEWAY * S];
+    const uint32_t net = so[SOA_NET * S], mask = so[SOA_MASK * S], hp_ip = so[SOA_HPIP * S], ports = so[SOA_PORTS * S];
+    const uint32_t hp_port = ports & 0xffffu, egress_port = ports >> 16;
+
+    const uint32_t ip = ingress ? src : dst, port = raw ? 0u : (ingress ? sport : dport);
+    const uint32_t hook = tcp ? CLK_HOOK_CONNECT4 : udp ? (ingress ? CLK_HOOK_RECVMSG4 : CLK_HOOK_SENDMSG4) : CLK_HOOK_SOCK_CREATE;
+    const bool recv = udp && ingress;
+    const bool act = uid != 0;                                                    // common.h:259-261
+    const bool byp = (fl & CLK_ROW_BYPASS) != 0, enf = (fl & CLK_ROW_ENFORCED) != 0;
+    const bool m_byp = act && !recv && byp;                                       // :265-271
+    const bool live = act && enf && !m_byp;                                       // :273-279
+
+    uint32_t verdict = CLK_V_PASS, metric = m_byp ? CLK_M_BYPASS : CLK_M_NONE, nip = 0, nport = 0, mh = 0, mp = 0;
+    if (live) {
+        if (raw) { verdict = CLK_V_DENY; metric = CLK_M_DENY; }                   // sock_create, clawker.c:235-238
+        else if (recv) {                                                          // recvmsg4, clawker.c:119-122
+            if (ip == coredns && port == 53) { verdict = CLK_V_REWRITE; nip = DOCKER_DNS_NBO; nport = 53; }
+        } else if (!(tcp && mark == CLAWKER_MARK_)) {                             // decide_connect :332-335 (connect only)
+            if (port == 53) {                                                     // :339-345 / :423-428
+                verdict = CLK_V_REWRITE; nip = coredns; nport = 53;
+                if (tcp) { metric = CLK_M_ALLOW; mp = 53; }
+            } else if ((ip & 0xffu) != 0x7fu && (ip & mask) != net && !cidr_hit(T, tb, ip)) {     // :347-351 (+A12)
+                if (udp) { verdict = CLK_V_DENY; metric = CLK_M_DENY; mp = port; }             // decide_sendmsg :436-437
+                else if (hp_ip != 0 && ip == hp_ip && port == hp_port) { }                     // :353-355
+                else if (ip == gateway) {                                                      // :362-370
+                    if (!(hp_port != 0 && port == hp_port)) { verdict = CLK_V_REWRITE; nip = envoy; nport = egress_port; metric = CLK_M_DENY; mp = port; }
+                } else {                                                                       // :386-409
+                    uint32_t hash = 0, eport = egress_port;
+                    if (dns_lookup(T, tb, ip, hash)) route_lookup(tb, hash, port, eport);
+                    verdict = CLK_V_REWRITE; nip = envoy; nport = eport; metric = CLK_M_ALLOW; mh = hash; mp = port;
+                }
+            }
         }
     }
+    if (verdict == CLK_V_REWRITE && nip == ip && nport == port) verdict = CLK_V_PASS;          // identity rewrite
+    uint32_t w = verdict | (metric << 2) | (hook << 24);
+    if (verdict == CLK_V_REWRITE) {
+        if (enf) w |= target_of(coredns, envoy, egress_port, nip, nport) << 6;
+        w |= (nport & 0xffffu) << 8;
+    }
+    word = w;
+    if (metric) { hm = true; mk = ((unsigned long long)((mp & 0xffffu) | (so[SOA_CROW * S] << 16) | (metric << 30)) << 32) | mh; }   // == metric_pack
+    return true;
+}
+
+// Every warp runs its own pipeline: a private ring of kStages 2 KiB tiles (32 slots x 64 B, filled by
+// TMA and signalled through the warp's own mbarriers), so there is no CTA-wide barrier in the loop.
+// The tile is copied to registers as soon as it lands and refilled immediately, which is why one
+// stage per warp already keeps the copy engine ahead of the ALU work.  Rare packets go to a per-warp
+// queue that is classified 32 at a time with all lanes converged.
+template <int kStages, bool kSwizzle, int kMinBlocks>
+__global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(const __grid_constant__ DevTables T, const __grid_constant__ CUtensorMap map,
+                                                                const uint8_t *__restrict__ pkts, uint32_t stride,
+                                                                unsigned long long n, uint32_t flags, uint32_t *__restrict__ verdicts)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const SmemLayout L = smem_layout(T, FAST_WARPS * kStages * WTILE_BYTES, FAST_WARPS * WQ_CAP * 4, FAST_WARPS * kStages);
+    Tabs tb; MetricAgg ag;
+    cta_prologue(T, smem, L, FAST_WARPS * kStages, tb, ag);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint64_t *bars = (uint64_t *)(smem + L.bars) + warp * kStages;
+    uint8_t *tiles = smem + L.tiles + warp * (kStages * WTILE_BYTES);
+    uint32_t *queue = (uint32_t *)(smem + L.queue) + warp * WQ_CAP;
+    const unsigned long long n_tiles = (n + 31ull) >> 5;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * FAST_WARPS + warp, W = (unsigned long long)gridDim.x * FAST_WARPS;
+    const bool do_metrics = !(flags & CLK_F_NO_METRICS);
+    const uint32_t gflags = flags & ~CLK_F_NAME_STAGE;
+    __syncthreads();                                         // tables staged, aggregation table zeroed, barriers initialised
+
+    if (lane == 0) {
+        for (int s = 0; s < kStages; s++) {
+            unsigned long long t = gw + (unsigned long long)s * W;
+            if (t < n_tiles) { mbar_expect_tx(&bars[s], WTILE_BYTES); tma_load_2d(tiles + s * WTILE_BYTES, &map, &bars[s], 0, (int)(t << 5)); }
+        }
+    }
+    uint32_t qn = 0;                                         // entries in this warp's queue (warp-uniform)
     uint32_t it = 0;
-    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+    for (unsigned long long t = gw; t < n_tiles; t += W, it++) {
         const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
         mbar_wait(&bars[s], ph);
-        const uint8_t *tile = smem + L.tiles + s * TILE_BYTES + tid * 64;
-        const uint32_t x = kSwizzle ? ((tid >> 1) & 3u) : 0u;                 // SWIZZLE_64B: chunk ^= (row >> 1) & 3
-        uint4 q0 = *(const uint4 *)(tile + ((0u ^ x) << 4));
-        uint4 q1 = *(const uint4 *)(tile + ((1u ^ x) << 4));
-        uint4 q2 = *(const uint4 *)(tile + ((2u ^ x) << 4));
-        uint4 q3 = *(const uint4 *)(tile + ((3u ^ x) << 4));
-        __syncthreads();                                                      // every lane has its 64 B in registers
-        if (tid == 0) {
-            unsigned long long tn = t + (unsigned long long)kStages * gridDim.x;
-            if (tn < n_tiles) { fence_proxy_async(); mbar_expect_tx(&bars[s], TILE_BYTES); tma_load_2d(smem + L.tiles + s * TILE_BYTES, &map, &bars[s], 0, (int)(tn * TILE_PKTS)); }
+        const uint8_t *slot = tiles + s * WTILE_BYTES + lane * 64;
+        const uint32_t x = kSwizzle ? ((lane >> 1) & 3u) : 0u;               // SWIZZLE_64B: chunk ^= (row >> 1) & 3
+        const uint32_t w3 = *(const uint32_t *)(slot + ((0u ^ x) << 4) + 12);
+        const uint4 q1 = *(const uint4 *)(slot + ((1u ^ x) << 4));
+        const uint2 q2 = *(const uint2 *)(slot + ((2u ^ x) << 4));
+        __syncwarp();                                                        // every lane holds its header words
+        if (lane == 0) {
+            unsigned long long tn = t + (unsigned long long)kStages * W;
+            if (tn < n_tiles) { fence_proxy_async(); mbar_expect_tx(&bars[s], WTILE_BYTES); tma_load_2d(tiles + s * WTILE_BYTES, &map, &bars[s], 0, (int)(tn << 5)); }
         }
-        const unsigned long long i = t * TILE_PKTS + tid;
-        Parsed p; Decision d; bool hm = false; unsigned long long mk = 0; uint32_t w = 0;
+        const unsigned long long i = (t << 5) + lane;
+        bool hm = false, slow = false; unsigned long long mk = 0; uint32_t w = 0;
         if (i < n) {
-            parse_headers(T, q0, q1, q2, q3, stride, flags & ~CLK_F_NAME_STAGE, p);
-            if (p.hook == 0xffu) finish_long_options(T, pkts + i * stride, stride, flags & ~CLK_F_NAME_STAGE, p);   // IPv4 options pushed L4 past byte 64
-            if (classify_parsed(T, lk, p, d, hm, mk)) w = make_word(d, &p.row->cfg, (p.row->flags & CLK_ROW_ENFORCED) != 0, p.hook, 0, 0);
-            stg_stream(&verdicts[i], w);
+            slow = !fast_classify(T, tb, w3, q1, q2.x, q2.y, w, hm, mk);
+            if (!slow) stg_stream(&verdicts[i], w);
+        }
+        const unsigned sm = __ballot_sync(0xffffffffu, slow);
+        if (sm) {
+            if (slow) queue[qn + __popc(sm & ((1u << lane) - 1u))] = (uint32_t)i;
+            qn += __popc(sm);
+            __syncwarp();
         }
         if (do_metrics) metric_warp_emit(T, ag, hm, mk);
+        if (qn >= 32) {                                                      // 32 rare packets: classify them converged
+            const unsigned long long j = queue[lane];
+            const uint32_t carry = lane + 32 < qn ? queue[lane + 32] : 0;
+            bool hm2 = false; unsigned long long mk2 = 0;
+            stg_stream(&verdicts[j], generic_one(T, tb, pkts + j * stride, stride, gflags, hm2, mk2));
+            if (do_metrics) metric_warp_emit(T, ag, hm2, mk2);
+            __syncwarp();
+            if (lane + 32 < qn) queue[lane] = carry;
+            qn -= 32;
+            __syncwarp();
+        }
+    }
+    {                                                                        // leftovers (< 32)
+        bool hm2 = false; unsigned long long mk2 = 0;
+        if (lane < qn) {
+            const unsigned long long j = queue[lane];
+            stg_stream(&verdicts[j], generic_one(T, tb, pkts + j * stride, stride, gflags, hm2, mk2));
+        }
+        if (do_metrics) metric_warp_emit(T, ag, hm2, mk2);
     }
     if (do_metrics) metric_cta_flush(T, ag);
 }
@@ -532,34 +691,20 @@ __global__ void __launch_bounds__(256) k_generic(const __grid_constant__ DevTabl
                                                  uint32_t flags, uint32_t *__restrict__ verdicts)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemLayout L = smem_layout(T.stage_dns_bytes, T.stage_route_bytes, 0, 0);
-    Lk lk; MetricAgg ag;
-    cta_prologue(T, smem, L, lk, ag);
+    const SmemLayout L = smem_layout(T, 0, 0, 0);
+    Tabs tb; MetricAgg ag;
+    cta_prologue(T, smem, L, 0, tb, ag);
+    __syncthreads();
     const bool do_metrics = !(flags & CLK_F_NO_METRICS);
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long n_round = (n + 31ull) & ~31ull;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += step) {
-        Parsed p; Decision d; bool hm = false; unsigned long long mk = 0;
+        bool hm = false; unsigned long long mk = 0;
         if (i < n) {
             const uint8_t *pk; uint32_t avail;
             if (kVarlen) { uint32_t o0 = __ldg(&offs16[i]), o1 = __ldg(&offs16[i + 1]); pk = pkts + (unsigned long long)o0 * 16ull; avail = (o1 - o0) * 16u; }
             else { pk = pkts + i * stride; avail = stride; }
-            uint4 z = make_uint4(0, 0, 0, 0), q0 = z, q1 = z, q2 = z, q3 = z;
-            const uint4 *pq = (const uint4 *)pk;
-            if (avail >= 16) q0 = __ldg(pq);
-            if (avail >= 32) q1 = __ldg(pq + 1);
-            if (avail >= 48) q2 = __ldg(pq + 2);
-            if (avail >= 64) q3 = __ldg(pq + 3);
-            parse_headers(T, q0, q1, q2, q3, avail, flags, p);
-            uint32_t w = 0;
-            if (p.hook == 0xffu) finish_long_options(T, pk, avail, flags, p);                 // IPv4 options pushing L4 past 64 B
-            if (p.ans_candidate) {
-                w = dns_answer_word(T, pk, p);
-            } else if (classify_parsed(T, lk, p, d, hm, mk)) {
-                uint32_t name = (flags & CLK_F_NAME_STAGE) ? name_stage(T, pk, avail, p, d) : CLK_N_NA;
-                w = make_word(d, &p.row->cfg, (p.row->flags & CLK_ROW_ENFORCED) != 0, p.hook, name, 0);
-            }
-            stg_stream(&verdicts[i], w);
+            stg_stream(&verdicts[i], generic_one(T, tb, pk, avail, flags, hm, mk));
         }
         if (do_metrics) metric_warp_emit(T, ag, hm, mk);
     }
@@ -573,9 +718,10 @@ __global__ void __launch_bounds__(256) k_events(const __grid_constant__ DevTable
                                                 unsigned long long n, uint32_t flags, uint32_t *__restrict__ verdicts)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemLayout L = smem_layout(T.stage_dns_bytes, T.stage_route_bytes, 0, 0);
-    Lk lk; MetricAgg ag;
-    cta_prologue(T, smem, L, lk, ag);
+    const SmemLayout L = smem_layout(T, 0, 0, 0);
+    Tabs tb; MetricAgg ag;
+    cta_prologue(T, smem, L, 0, tb, ag);
+    __syncthreads();
     const bool do_metrics = !(flags & CLK_F_NO_METRICS);
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long n_round = (n + 31ull) & ~31ull;
@@ -594,7 +740,7 @@ __global__ void __launch_bounds__(256) k_events(const __grid_constant__ DevTable
             const uint32_t ip = six ? e.user_ip6[3] : e.user_ip4;
             uint32_t w = 0;
             if (cr) {
-                run_hooks(T, lk, e.hook, e.sock_type, e.uid, e.so_mark, cr->flags, &cr->cfg, ip, e.user_port,
+                run_hooks(T, tb, e.hook, e.sock_type, e.uid, e.so_mark, cr->flags, &cr->cfg, ip, e.user_port,
                           e.user_ip6[0], e.user_ip6[1], e.user_ip6[2], d);
                 if (d.verdict == CLK_V_REWRITE && d.new_ip == ip && d.new_port == e.user_port) d.verdict = CLK_V_PASS;
                 if (d.metric) { hm = true; mk = metric_pack(d.m_hash, d.m_port, crow, d.metric - 1); }
@@ -626,8 +772,8 @@ __global__ void __launch_bounds__(256) k_dns_extract(const __grid_constant__ Dev
     }
 }
 
-// per-packet update counts -> exclusive prefix positions (single pass, decoupled look-back is overkill here:
-// counts are tiny and the array is streamed once; a 3-kernel block scan keeps it simple and deterministic)
+// per-packet update counts -> exclusive prefix positions (counts are tiny and the array is streamed
+// once; a block-sum / serial-scan / per-block-scan trio keeps it simple and deterministic)
 __global__ void __launch_bounds__(256) k_count_block(const uint32_t *__restrict__ verdicts, unsigned long long n, unsigned long long *__restrict__ block_sums)
 {
     __shared__ unsigned long long sh[8];
@@ -645,7 +791,6 @@ __global__ void k_scan_blocks(unsigned long long *block_sums, uint32_t nb, unsig
 __global__ void __launch_bounds__(256) k_positions(const uint32_t *__restrict__ verdicts, unsigned long long n,
                                                    const unsigned long long *__restrict__ block_sums, unsigned long long *__restrict__ out_pos)
 {
-    // sequential inside a block of 4096 by one warp-wide scan per 32 items
     __shared__ unsigned long long carry;
     unsigned long long base = (unsigned long long)blockIdx.x * 4096ull;
     if (threadIdx.x == 0) carry = block_sums[blockIdx.x];
@@ -688,7 +833,6 @@ __global__ void k_counters_import(const __grid_constant__ DevTables T, const clk
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (unsigned long long)gridDim.x * blockDim.x) {
         clk_metric m = blocks[i];
         if (m.count == 0) continue;
-        // cgroup_id -> local crow
         uint32_t h = mix64(m.key.cgroup_id) & T.cg_mask, crow = 0xffffffffu;
         if (T.n_crows) for (;;) { uint32_t s = T.cg_slots[h]; if (!s) break; if (T.crows[s - 1].cgroup_id == m.key.cgroup_id) { crow = s - 1; break; } h = (h + 1) & T.cg_mask; }
         if (crow == 0xffffffffu) { atomicAdd(T.m_dropped, m.count); continue; }
@@ -733,14 +877,29 @@ static cudaError_t occupancy_grid(K kernel, int threads, size_t smem, int *grid)
     return cudaSuccess;
 }
 
+template <int kStages, bool kSwizzle, int kMinBlocks>
+static const char *launch_fast(const DevTables &T, const CUtensorMap &map, const void *d_pkts, uint32_t stride, unsigned long long n,
+                               uint32_t flags, uint32_t *d_verdicts, cudaStream_t st, LaunchInfo *info)
+{
+    int grid = 0; cudaError_t e;
+    SmemLayout L = smem_layout(T, FAST_WARPS * kStages * WTILE_BYTES, FAST_WARPS * WQ_CAP * 4, FAST_WARPS * kStages);
+    if ((e = occupancy_grid(k_slots_fast<kStages, kSwizzle, kMinBlocks>, FAST_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
+    unsigned long long n_cta = ((n + 31) / 32 + FAST_WARPS - 1) / FAST_WARPS;
+    if ((unsigned long long)grid > n_cta) grid = (int)n_cta;
+    k_slots_fast<kStages, kSwizzle, kMinBlocks><<<grid, FAST_WARPS * 32, L.total, st>>>(T, map, (const uint8_t *)d_pkts, stride, n, flags, d_verdicts);
+    if (info) { info->grid = grid; info->block = FAST_WARPS * 32; info->smem = L.total; }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride, unsigned long long n, uint32_t flags,
-                         uint32_t *d_verdicts, cudaStream_t st, int loader, LaunchInfo *info)
+                         uint32_t *d_verdicts, cudaStream_t st, int loader, int stages, LaunchInfo *info)
 {
     if (n == 0) return nullptr;
     cudaError_t e;
     int grid = 0;
     if (loader == LOADER_DIRECT || (flags & CLK_F_NAME_STAGE) || n >= 0x7fffffffull || stride > 0xffff0u) {
-        SmemLayout L = smem_layout(T.stage_dns_bytes, T.stage_route_bytes, 0, 0);
+        SmemLayout L = smem_layout(T, 0, 0, 0);
         if ((e = occupancy_grid(k_generic<false>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
         unsigned long long need = (n + 255) / 256; if ((unsigned long long)grid > need) grid = (int)need;
         k_generic<false><<<grid, 256, L.total, st>>>(T, (const uint8_t *)d_pkts, nullptr, stride, n, flags, d_verdicts);
@@ -753,27 +912,20 @@ const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride
     CUtensorMap map;
     cuuint64_t gdim[2] = { stride, n };
     cuuint64_t gstr[1] = { stride };
-    cuuint32_t box[2] = { 64, TILE_PKTS };
+    cuuint32_t box[2] = { 64, 32 };                      // one warp's tile: 32 slots x 64 B
     cuuint32_t estr[2] = { 1, 1 };
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(d_pkts), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      loader == LOADER_TMA_SW64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed";
-    const int stages = 3;
-    SmemLayout L = smem_layout(T.stage_dns_bytes, T.stage_route_bytes, TILE_BYTES, stages);
-    unsigned long long n_tiles = (n + TILE_PKTS - 1) / TILE_PKTS;
-    if (loader == LOADER_TMA_SW64) {
-        if ((e = occupancy_grid(k_slots_tma<3, true>, TILE_PKTS, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
-        if ((unsigned long long)grid > n_tiles) grid = (int)n_tiles;
-        k_slots_tma<3, true><<<grid, TILE_PKTS, L.total, st>>>(T, map, (const uint8_t *)d_pkts, stride, n, flags, d_verdicts);
-    } else {
-        if ((e = occupancy_grid(k_slots_tma<3, false>, TILE_PKTS, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
-        if ((unsigned long long)grid > n_tiles) grid = (int)n_tiles;
-        k_slots_tma<3, false><<<grid, TILE_PKTS, L.total, st>>>(T, map, (const uint8_t *)d_pkts, stride, n, flags, d_verdicts);
-    }
-    if (info) { info->grid = grid; info->block = TILE_PKTS; info->smem = L.total; }
-    e = cudaGetLastError();
-    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+#define FAST_ARGS T, map, d_pkts, stride, n, flags, d_verdicts, st, info
+    const int minb = stages >> 4; stages &= 15;              // stages | minblocks << 4 (tuning knob CLK_STAGES / CLK_MINB)
+    if (loader != LOADER_TMA_SW64) return launch_fast<2, false, 2>(FAST_ARGS);
+    if (minb >= 3) return stages <= 1 ? launch_fast<1, true, 3>(FAST_ARGS) : launch_fast<2, true, 3>(FAST_ARGS);
+    if (stages <= 1) return launch_fast<1, true, 2>(FAST_ARGS);
+    if (stages == 2) return launch_fast<2, true, 2>(FAST_ARGS);
+    return launch_fast<3, true, 2>(FAST_ARGS);
+#undef FAST_ARGS
 }
 
 const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n, uint32_t flags,
@@ -781,7 +933,7 @@ const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t
 {
     if (n == 0) return nullptr;
     int grid = 0; cudaError_t e;
-    SmemLayout L = smem_layout(T.stage_dns_bytes, T.stage_route_bytes, 0, 0);
+    SmemLayout L = smem_layout(T, 0, 0, 0);
     if ((e = occupancy_grid(k_generic<true>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long need = (n + 255) / 256; if ((unsigned long long)grid > need) grid = (int)need;
     k_generic<true><<<grid, 256, L.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, 0, n, flags, d_verdicts);
@@ -795,7 +947,7 @@ const char *launch_events(const DevTables &T, const clk_event *d_ev, unsigned lo
 {
     if (n == 0) return nullptr;
     int grid = 0; cudaError_t e;
-    SmemLayout L = smem_layout(T.stage_dns_bytes, T.stage_route_bytes, 0, 0);
+    SmemLayout L = smem_layout(T, 0, 0, 0);
     if ((e = occupancy_grid(k_events, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long need = (n + 255) / 256; if ((unsigned long long)grid > need) grid = (int)need;
     k_events<<<grid, 256, L.total, st>>>(T, d_ev, n, flags, d_verdicts);

@@ -22,6 +22,10 @@ CLK_HD uint32_t mix32(uint32_t x)
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
+#if !defined(__CUDACC__)
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+#endif
 CLK_HD uint32_t mix64(uint64_t x)
 {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
@@ -76,10 +80,23 @@ struct NameSlot {
     uint32_t str_off;           // offset into names blob: [len u8][bytes]
 };
 
-// ---- dns_cache / route_map slots -------------------------------------------------------------
-// dns slot  : lo32 = ip (key), hi32 = domain_hash.             empty = ~0ull
-// route slot: [63:32] domain_hash, [31:16] dst_port, [15:0] envoy_port.   empty = ~0ull
+// ---- dns_cache / route_map: 2-choice bucketed tables -------------------------------------------
+// A bucket is one 16-byte word holding two 8-byte slots, so a lookup is one 128-bit load and a
+// miss is decided without a probe loop: keys go to bucket b1 while it has room, else to b2.
+//   dns slot  : lo32 = ip (key), hi32 = domain_hash.                       empty = ~0ull
+//   route slot: [63:32] domain_hash, [31:16] dst_port, [15:0] envoy_port.  empty = ~0ull
 static const uint64_t SLOT_EMPTY = ~0ull;
+// Table hashes are a single multiply whose TOP bits index the table (index = hash >> shift, with
+// shift = 32 - log2(size)): the tables are rebuilt (and grown) by the host until every key fits, so
+// hash quality only affects table size, never correctness.
+CLK_HD uint32_t hash_a(uint32_t x) { return x * 0x9E3779B1u; }
+CLK_HD uint32_t hash_b(uint32_t x) { return (x ^ 0x68E31DA4u) * 0x85EBCA77u; }
+CLK_HD uint32_t route_fold(uint32_t hash, uint32_t port) { return hash ^ (port * 0x01000193u); }
+CLK_HD uint32_t shift_for(uint32_t size_pow2) { uint32_t k = 0; while ((1u << k) < size_pow2) k++; return 32u - k; }
+
+// Endpoint rows again as structure-of-arrays (one u32 array per field, `soa_stride` apart) so that a
+// warp reading one field of 32 different rows from shared memory hits 32 different banks.
+enum { SOA_UID = 0, SOA_MARK, SOA_FLAGS, SOA_ENVOY, SOA_COREDNS, SOA_GATEWAY, SOA_NET, SOA_MASK, SOA_HPIP, SOA_PORTS /* hp_port | egress << 16 */, SOA_CROW, SOA_FIELDS = 12 };
 
 // ---- metrics (per-GPU metrics_map) -----------------------------------------------------------
 // Packed key: [31:0] domain_hash, [47:32] dst_port, [61:48] crow, [63:62] action+1 (never 0).
@@ -93,17 +110,19 @@ CLK_HD uint64_t metric_pack(uint32_t hash, uint32_t port, uint32_t crow, uint32_
 // ---- the snapshot handed to kernels by value -------------------------------------------------
 struct DevTables {
     const EpRow    *ep_rows;     uint32_t n_ep_rows;
-    const uint32_t *ep_slots;    uint32_t ep_mask;       // slot: EpRow index + 1 (0 empty), keyed by mix32(ip)
+    const uint2    *ep_slots;    uint32_t ep_mask, ep_shift;   // slot: {ip, EpRow index + 1} (y == 0 empty), index hash_a(ip) >> ep_shift, load <= 1/4
+    const uint32_t *ep_soa;      uint32_t soa_stride;    // SOA_FIELDS arrays of soa_stride words, indexed by EpRow index
     const Ep6Key   *ep6;         uint32_t n_ep6;         // linear (<= 256 rows), rarely non-empty
     const ContRow  *crows;       uint32_t n_crows;
     const uint32_t *cg_slots;    uint32_t cg_mask;       // slot: ContRow index + 1, keyed by mix64(cgroup_id)
-    const uint64_t *dns_slots;   uint32_t dns_mask;      // 0 mask + null => empty table
-    const uint64_t *route_slots; uint32_t route_mask;
+    const uint4    *dns_b;       uint32_t dns_shift;     // buckets; null => empty table; index hash_{a,b}(ip) >> dns_shift
+    const uint4    *route_b;     uint32_t route_shift;
     uint32_t dns_ffff_present;   uint32_t dns_ffff_hash; // the one key/value pair that equals SLOT_EMPTY
     // CIDR allow set (A12): 2 bits per /24 block: bit0 = covered by a prefix <= /24,
     // bit1 = block has longer prefixes -> cidr_l2 (hash by block -> 256-bit host bitmap)
     const uint32_t *cidr_l1;     uint32_t n_cidr;        // n_cidr == 0 => stage skipped
-    const uint32_t *cidr_l2_keys; const uint32_t *cidr_l2_bits; uint32_t cidr_l2_mask;   // key: block+1; bits: 8 words / slot
+    const uint32_t *cidr_pre;                            // 64 Kbit prefilter: bit (addr >> 16) set iff some rule intersects that /16
+    const uint32_t *cidr_l2_keys; const uint32_t *cidr_l2_bits; uint32_t cidr_l2_mask, cidr_l2_shift;   // key: block+1; bits: 8 words / slot
     const NameSlot *zone_slots;  uint32_t zone_mask;
     const NameSlot *sni_slots;   uint32_t sni_mask;
     const uint8_t  *names;                               // blob for string confirmation
@@ -112,7 +131,7 @@ struct DevTables {
     unsigned long long *m_keys;  unsigned long long *m_counts; uint32_t m_mask;
     unsigned long long *m_dropped;
     // sizes for optional shared-memory staging (bytes; 0 = do not stage)
-    uint32_t stage_dns_bytes, stage_route_bytes;
+    uint32_t stage_ep_bytes, stage_soa_bytes, stage_dns_bytes, stage_route_bytes, stage_pre_bytes;
 };
 
 }  // namespace clk

@@ -47,8 +47,8 @@ struct DevBuf {
 };
 
 struct Snapshot {
-    DevBuf ep_rows, ep_slots, ep6, crows, cg_slots, dns, route, cidr_l1, cidr_l2_keys, cidr_l2_bits, zone, sni, names;
-    void release() { for (DevBuf *b : { &ep_rows, &ep_slots, &ep6, &crows, &cg_slots, &dns, &route, &cidr_l1, &cidr_l2_keys, &cidr_l2_bits, &zone, &sni, &names }) b->release(); }
+    DevBuf ep_rows, ep_slots, ep_soa, ep6, crows, cg_slots, dns, route, cidr_pre, cidr_l1, cidr_l2_keys, cidr_l2_bits, zone, sni, names;
+    void release() { for (DevBuf *b : { &ep_rows, &ep_slots, &ep_soa, &ep6, &crows, &cg_slots, &dns, &route, &cidr_pre, &cidr_l1, &cidr_l2_keys, &cidr_l2_bits, &zone, &sni, &names }) b->release(); }
 };
 
 struct MetricKeyHash {
@@ -91,6 +91,7 @@ struct clk_engine {
     DevBuf work_pkts[3], work_offs[3], work_verd[3], scan_sums, scan_pos, scan_total, upd_out, ctr_block;
     clk_stats stats;
     int loader = LOADER_TMA_SW64;
+    int stages = 3;
     bool stage_tables = true;
     uint64_t chunk_pkts = 1u << 21;
 
@@ -203,11 +204,12 @@ int publish_locked(clk_engine *e)
         if (it != e->crow_of.end()) { r.crow = it->second; r.flags = crows[it->second].flags; r.cfg = crows[it->second].cfg; }
     };
     for (auto &kv : e->endpoint) { EpRow r; memset(&r, 0, sizeof r); r.ip = kv.first; fill(r, kv.second); rows.push_back(r); }
-    std::vector<uint32_t> ep_slots(pow2_at_least(rows.size() * 2 + 1), 0);
-    for (size_t i = 0; i < rows.size(); i++) {
-        uint32_t h = mix32(rows[i].ip) & (uint32_t)(ep_slots.size() - 1);
-        while (ep_slots[h]) h = (h + 1) & (uint32_t)(ep_slots.size() - 1);
-        ep_slots[h] = (uint32_t)i + 1;
+    const size_t n_ep4 = rows.size();
+    std::vector<uint2> ep_slots(pow2_at_least(n_ep4 * 4 + 1), uint2{ 0, 0 });      // load <= 1/4: probe loops stay ~1 iteration
+    for (size_t i = 0; i < n_ep4; i++) {
+        uint32_t h = hash_a(rows[i].ip) >> shift_for((uint32_t)ep_slots.size());
+        while (ep_slots[h].y) h = (h + 1) & (uint32_t)(ep_slots.size() - 1);
+        ep_slots[h] = uint2{ rows[i].ip, (uint32_t)i + 1 };
     }
     for (auto &kv : e->endpoint6) {
         EpRow r; memset(&r, 0, sizeof r); fill(r, kv.second);
@@ -215,33 +217,64 @@ int publish_locked(clk_engine *e)
         rows.push_back(r); ep6.push_back(k);
     }
     // ---- dns_cache / route_map --------------------------------------------------------------------
-    std::vector<uint64_t> dns_slots, route_slots;
+    // 2-choice bucketed tables (dev_tables.h): grow until every key fits one of its two buckets
+    std::vector<uint4> dns_b, route_b;
+    auto slot_empty = [](const uint4 &b, int k) { return k == 0 ? (b.x & b.y) == 0xffffffffu : (b.z & b.w) == 0xffffffffu; };
+    auto slot_put = [](uint4 &b, int k, uint64_t s) { if (k == 0) { b.x = (uint32_t)s; b.y = (uint32_t)(s >> 32); } else { b.z = (uint32_t)s; b.w = (uint32_t)(s >> 32); } };
+    // items: (slot word, (hash_a, hash_b) of the key).  Invariant the lookup relies on: a key sits in its
+    // second bucket only while its first bucket is full.  One level of displacement (move a resident whose
+    // FIRST bucket this is over to its second bucket) keeps tables at ~0.4 load.
+    auto build_buckets = [&](std::vector<uint4> &out, const std::vector<std::pair<uint64_t, std::pair<uint32_t, uint32_t>>> &items) {
+        uint32_t nb = pow2_at_least((uint64_t)items.size() * 5 / 6 + 1);
+        for (;; nb *= 2) {
+            const uint32_t sh = shift_for(nb);
+            out.assign(nb, uint4{ 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu });
+            std::vector<int> owner((size_t)nb * 2, -1);                  // item index per slot
+            auto place = [&](uint32_t b, int idx) -> bool {
+                for (int k = 0; k < 2; k++) if (slot_empty(out[b], k)) { slot_put(out[b], k, items[idx].first); owner[(size_t)b * 2 + k] = idx; return true; }
+                return false;
+            };
+            bool ok = true;
+            for (int idx = 0; idx < (int)items.size() && ok; idx++) {
+                const uint32_t b1 = items[idx].second.first >> sh, b2 = items[idx].second.second >> sh;
+                if (place(b1, idx) || place(b2, idx)) continue;
+                bool moved = false;
+                for (uint32_t b : { b1, b2 }) {
+                    for (int k = 0; k < 2 && !moved; k++) {
+                        int j = owner[(size_t)b * 2 + k];
+                        if (j < 0 || (items[j].second.first >> sh) != b) continue;          // only residents in their first bucket may move
+                        uint32_t jb2 = items[j].second.second >> sh;
+                        if (jb2 != b && place(jb2, j)) { slot_put(out[b], k, items[idx].first); owner[(size_t)b * 2 + k] = idx; moved = true; }
+                    }
+                    if (moved) break;
+                }
+                ok = moved;
+            }
+            if (ok) break;
+        }
+    };
     if (!e->dns.empty()) {
-        dns_slots.assign(pow2_at_least(e->dns.size() * 2 + 1), SLOT_EMPTY);
-        uint32_t mask = (uint32_t)dns_slots.size() - 1;
+        std::vector<std::pair<uint64_t, std::pair<uint32_t, uint32_t>>> items;
         for (auto &kv : e->dns) {
             uint64_t s = (uint64_t)kv.first | ((uint64_t)kv.second.domain_hash << 32);
             if (s == SLOT_EMPTY) { T.dns_ffff_present = 1; T.dns_ffff_hash = 0xffffffffu; continue; }
-            uint32_t h = mix32(kv.first) & mask;
-            while (dns_slots[h] != SLOT_EMPTY) h = (h + 1) & mask;
-            dns_slots[h] = s;
+            items.push_back({ s, { hash_a(kv.first), hash_b(kv.first) } });
         }
+        if (!items.empty()) build_buckets(dns_b, items);
     }
     if (!e->route.empty()) {
-        route_slots.assign(pow2_at_least(e->route.size() * 2 + 1), SLOT_EMPTY);
-        uint32_t mask = (uint32_t)route_slots.size() - 1;
+        std::vector<std::pair<uint64_t, std::pair<uint32_t, uint32_t>>> items;
         for (auto &kv : e->route) {
-            uint64_t s = (kv.first << 16) | kv.second;
-            uint32_t h = mix64(kv.first) & mask;
-            while (route_slots[h] != SLOT_EMPTY) h = (h + 1) & mask;
-            route_slots[h] = s;
+            uint32_t hash = (uint32_t)(kv.first >> 16), port = (uint32_t)(kv.first & 0xffff), f = route_fold(hash, port);
+            items.push_back({ (kv.first << 16) | kv.second, { hash_a(f), hash_b(f) } });
         }
+        build_buckets(route_b, items);
     }
     // ---- CIDR directory (A12) ---------------------------------------------------------------------
-    std::vector<uint32_t> l1, l2_keys, l2_bits;
+    std::vector<uint32_t> l1, l2_keys, l2_bits, pre;
     uint32_t n_cidr = 0;
     if (!e->cidr.empty()) {
-        l1.assign((1u << 24) / 16, 0);
+        l1.assign((1u << 24) / 16, 0); pre.assign(65536 / 32, 0);
         std::unordered_map<uint32_t, std::array<uint32_t, 8>> leaves;
         for (auto &kv : e->cidr) {
             uint32_t addr = kv.first.first, mask = kv.first.second;
@@ -249,6 +282,10 @@ int publish_locked(clk_engine *e)
             n_cidr++;
             int plen = mask_plen(mask);
             uint32_t base = __builtin_bswap32(addr);       // host-order network
+            {   // /16 prefilter
+                uint32_t p0 = base >> 16, pc = plen >= 16 ? 1u : 1u << (16 - plen);
+                for (uint32_t p = p0; p < p0 + pc; p++) pre[p >> 5] |= 1u << (p & 31);
+            }
             if (plen <= 24) {
                 uint32_t b0 = base >> 8, cnt = 1u << (24 - plen);
                 for (uint32_t b = b0; b < b0 + cnt; b++) l1[b >> 4] |= 1u << ((b & 15) * 2);
@@ -262,12 +299,12 @@ int publish_locked(clk_engine *e)
         uint32_t cap = pow2_at_least(leaves.size() * 2 + 1);
         l2_keys.assign(cap, 0); l2_bits.assign((size_t)cap * 8, 0);
         for (auto &kv : leaves) {
-            uint32_t h = mix32(kv.first) & (cap - 1);
+            uint32_t h = hash_a(kv.first) >> shift_for(cap);
             while (l2_keys[h]) h = (h + 1) & (cap - 1);
             l2_keys[h] = kv.first + 1;
             memcpy(&l2_bits[(size_t)h * 8], kv.second.data(), 32);
         }
-        if (n_cidr == 0) { l1.clear(); l2_keys.clear(); l2_bits.clear(); }
+        if (n_cidr == 0) { l1.clear(); l2_keys.clear(); l2_bits.clear(); pre.clear(); }
     }
     // ---- name tables --------------------------------------------------------------------------------
     std::vector<NameSlot> zone_slots, sni_slots; std::vector<uint8_t> blob;
@@ -281,24 +318,38 @@ int publish_locked(clk_engine *e)
     }
     // ---- upload -------------------------------------------------------------------------------------
     CUDA_TRY(e, upload(S.crows, crows, st));       CUDA_TRY(e, upload(S.cg_slots, cg_slots, st));
+    // structure-of-arrays copy of the endpoint rows (dev_tables.h SOA_*), at least one zero row
+    const uint32_t soa_stride = (uint32_t)((std::max<size_t>(rows.size(), 1) + 3) & ~(size_t)3);
+    std::vector<uint32_t> soa((size_t)SOA_FIELDS * soa_stride, 0);
+    for (size_t i = 0; i < rows.size(); i++) {
+        const EpRow &r = rows[i];
+        soa[SOA_UID * soa_stride + i] = r.uid; soa[SOA_MARK * soa_stride + i] = r.so_mark; soa[SOA_FLAGS * soa_stride + i] = r.flags;
+        soa[SOA_ENVOY * soa_stride + i] = r.cfg.envoy_ip; soa[SOA_COREDNS * soa_stride + i] = r.cfg.coredns_ip;
+        soa[SOA_GATEWAY * soa_stride + i] = r.cfg.gateway_ip; soa[SOA_NET * soa_stride + i] = r.cfg.net_addr;
+        soa[SOA_MASK * soa_stride + i] = r.cfg.net_mask; soa[SOA_HPIP * soa_stride + i] = r.cfg.host_proxy_ip;
+        soa[SOA_PORTS * soa_stride + i] = (uint32_t)r.cfg.host_proxy_port | ((uint32_t)r.cfg.egress_port << 16);
+        soa[SOA_CROW * soa_stride + i] = r.crow;
+    }
     CUDA_TRY(e, upload(S.ep_rows, rows, st));      CUDA_TRY(e, upload(S.ep_slots, ep_slots, st));
-    CUDA_TRY(e, upload(S.ep6, ep6, st));
-    CUDA_TRY(e, upload(S.dns, dns_slots, st));     CUDA_TRY(e, upload(S.route, route_slots, st));
+    CUDA_TRY(e, upload(S.ep_soa, soa, st));        CUDA_TRY(e, upload(S.ep6, ep6, st));
+    CUDA_TRY(e, upload(S.dns, dns_b, st));         CUDA_TRY(e, upload(S.route, route_b, st));
+    CUDA_TRY(e, upload(S.cidr_pre, pre, st));
     CUDA_TRY(e, upload(S.cidr_l1, l1, st));        CUDA_TRY(e, upload(S.cidr_l2_keys, l2_keys, st));
     CUDA_TRY(e, upload(S.cidr_l2_bits, l2_bits, st));
     CUDA_TRY(e, upload(S.zone, zone_slots, st));   CUDA_TRY(e, upload(S.sni, sni_slots, st));
     CUDA_TRY(e, upload(S.names, blob, st));
     CUDA_TRY(e, cudaStreamSynchronize(st));
 
-    T.ep_rows = rows.empty() ? nullptr : (const EpRow *)S.ep_rows.p; T.n_ep_rows = (uint32_t)e->endpoint.size();
-    T.ep_slots = (const uint32_t *)S.ep_slots.p; T.ep_mask = (uint32_t)ep_slots.size() - 1;
+    T.ep_rows = rows.empty() ? nullptr : (const EpRow *)S.ep_rows.p; T.n_ep_rows = (uint32_t)rows.size();
+    if (n_ep4) { T.ep_slots = (const uint2 *)S.ep_slots.p; T.ep_mask = (uint32_t)ep_slots.size() - 1; T.ep_shift = shift_for((uint32_t)ep_slots.size()); }
+    T.ep_soa = (const uint32_t *)S.ep_soa.p; T.soa_stride = soa_stride;
     T.ep6 = ep6.empty() ? nullptr : (const Ep6Key *)S.ep6.p; T.n_ep6 = (uint32_t)ep6.size();
     T.crows = crows.empty() ? nullptr : (const ContRow *)S.crows.p; T.n_crows = (uint32_t)crows.size();
     T.cg_slots = (const uint32_t *)S.cg_slots.p; T.cg_mask = (uint32_t)cg_slots.size() - 1;
-    if (!dns_slots.empty()) { T.dns_slots = (const uint64_t *)S.dns.p; T.dns_mask = (uint32_t)dns_slots.size() - 1; }
-    if (!route_slots.empty()) { T.route_slots = (const uint64_t *)S.route.p; T.route_mask = (uint32_t)route_slots.size() - 1; }
+    if (!dns_b.empty()) { T.dns_b = (const uint4 *)S.dns.p; T.dns_shift = shift_for((uint32_t)dns_b.size()); }
+    if (!route_b.empty()) { T.route_b = (const uint4 *)S.route.p; T.route_shift = shift_for((uint32_t)route_b.size()); }
     T.n_cidr = n_cidr;
-    if (n_cidr) { T.cidr_l1 = (const uint32_t *)S.cidr_l1.p; T.cidr_l2_keys = (const uint32_t *)S.cidr_l2_keys.p; T.cidr_l2_bits = (const uint32_t *)S.cidr_l2_bits.p; T.cidr_l2_mask = (uint32_t)l2_keys.size() - 1; }
+    if (n_cidr) { T.cidr_pre = (const uint32_t *)S.cidr_pre.p; T.cidr_l1 = (const uint32_t *)S.cidr_l1.p; T.cidr_l2_keys = (const uint32_t *)S.cidr_l2_keys.p; T.cidr_l2_bits = (const uint32_t *)S.cidr_l2_bits.p; T.cidr_l2_mask = (uint32_t)l2_keys.size() - 1; T.cidr_l2_shift = shift_for((uint32_t)l2_keys.size()); }
     if (!zone_slots.empty()) { T.zone_slots = (const NameSlot *)S.zone.p; T.zone_mask = (uint32_t)zone_slots.size() - 1; }
     if (!sni_slots.empty()) { T.sni_slots = (const NameSlot *)S.sni.p; T.sni_mask = (uint32_t)sni_slots.size() - 1; }
     T.names = (const uint8_t *)S.names.p;
@@ -311,10 +362,12 @@ int publish_locked(clk_engine *e)
     std::sort(T.coredns_ips, T.coredns_ips + T.n_coredns);
     T.m_keys = (unsigned long long *)e->m_keys.p; T.m_counts = (unsigned long long *)e->m_counts.p;
     T.m_mask = e->T.m_mask; T.m_dropped = (unsigned long long *)e->m_dropped.p;
-    // shared-memory staging budget: dns <= 32 KiB, route <= 8 KiB
+    // shared-memory staging budget: endpoints <= 256 rows, dns <= 32 KiB, route <= 8 KiB
     if (e->stage_tables) {
-        if (!dns_slots.empty() && dns_slots.size() * 8 <= 32768) T.stage_dns_bytes = (uint32_t)dns_slots.size() * 8;
-        if (!route_slots.empty() && route_slots.size() * 8 <= 8192) T.stage_route_bytes = (uint32_t)route_slots.size() * 8;
+        if (n_ep4 && rows.size() <= 256) { T.stage_ep_bytes = (uint32_t)ep_slots.size() * 8; T.stage_soa_bytes = (uint32_t)soa.size() * 4; }
+        if (!dns_b.empty() && dns_b.size() * 16 <= 32768) T.stage_dns_bytes = (uint32_t)dns_b.size() * 16;
+        if (!route_b.empty() && route_b.size() * 16 <= 8192) T.stage_route_bytes = (uint32_t)route_b.size() * 16;
+        if (n_cidr) T.stage_pre_bytes = 8192;
     }
     e->T = T; e->active = 1 - e->active; e->published = true; e->dirty = false;
     return CLK_OK;
@@ -364,6 +417,8 @@ int clk_engine_create(const clk_cfg *cfg, clk_engine **out)
     }
     if (const char *s = getenv("CLK_LOADER")) e->loader = atoi(s);
     if (const char *s = getenv("CLK_STAGE")) e->stage_tables = atoi(s) != 0;
+    if (const char *s = getenv("CLK_STAGES")) e->stages = atoi(s);
+    if (const char *s = getenv("CLK_MINB")) e->stages |= atoi(s) << 4;
     if (const char *s = getenv("CLK_CHUNK_PKTS")) { long v = atol(s); if (v >= 1024) e->chunk_pkts = (uint64_t)v; }
     if (!e->host_only) {
         int dev = cfg ? cfg->device : -1;
@@ -613,7 +668,7 @@ int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, u
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     LaunchInfo li = { 0, 0, 0 };
     cudaEventRecord(e->ev0, st);
-    const char *err = launch_slots(e->T, d_pkts, stride, n, flags, (uint32_t *)d_verdicts, st, e->loader, &li);
+    const char *err = launch_slots(e->T, d_pkts, stride, n, flags, (uint32_t *)d_verdicts, st, e->loader, e->stages, &li);
     cudaEventRecord(e->ev1, st);
     return finish_launch(e, err, li);
 }
@@ -662,7 +717,7 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
         } else {
             CUDA_TRY(e, e->work_pkts[s].ensure(cnt * stride));
             CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + done * stride, cnt * stride, cudaMemcpyHostToDevice, st));
-            err = launch_slots(e->T, e->work_pkts[s].p, stride, cnt, flags, (uint32_t *)e->work_verd[s].p, st, e->loader, &li);
+            err = launch_slots(e->T, e->work_pkts[s].p, stride, cnt, flags, (uint32_t *)e->work_verd[s].p, st, e->loader, e->stages, &li);
         }
         rc = finish_launch(e, err, li); if (rc) return rc;
         CUDA_TRY(e, cudaMemcpyAsync(verdicts + done, e->work_verd[s].p, cnt * 4, cudaMemcpyDeviceToHost, st));

@@ -15,24 +15,6 @@ __device__ __forceinline__ uint32_t gbe16(const uint8_t *p) { return (gb(p) << 8
 __device__ __forceinline__ uint32_t lower(uint32_t c) { return (c - 'A' < 26u) ? c + 32u : c; }
 __device__ __forceinline__ bool zone_char(uint32_t c) { return (c - 'a' < 26u) || (c - '0' < 10u) || c == '_' || c == '-'; }
 
-// Second half of the IPv4 parse once ports are known (shared by the 64 B fast path and long-option packets).
-__device__ __forceinline__ void finish_long_options(const DevTables &T, const uint8_t *pk, uint32_t avail, uint32_t flags, Parsed &p)
-{
-    uint32_t l4off = p.l4off, proto = p.proto, dst = p.ip, src = p.a0;
-    uint32_t sport = gbe16(pk + l4off), dport = gbe16(pk + l4off + 2);
-    p.hook = CLK_HOOK_NONE; p.ip = 0; p.a0 = 0;
-    const EpRow *row = ep_lookup4(T, src);
-    bool ingress = false;
-    if (!row && proto == 17) { row = ep_lookup4(T, dst); ingress = row != nullptr; }
-    if (!row) {
-        if (proto == 17 && sport == 53 && (flags & CLK_F_NAME_STAGE) && is_coredns(T, dst)) p.ans_candidate = true;
-        return;
-    }
-    p.row = row; p.ingress = ingress; p.ip = ingress ? src : dst;
-    if (proto == 6)       { p.hook = CLK_HOOK_CONNECT4; p.type = SOCK_STREAM_; p.port = dport; }
-    else if (proto == 17) { p.type = SOCK_DGRAM_; if (ingress) { p.hook = CLK_HOOK_RECVMSG4; p.port = sport; } else { p.hook = CLK_HOOK_SENDMSG4; p.port = dport; } }
-}
-
 // ---- DNS name walker (RFC 1035 §4.1.4; limits of miekg/dns UnpackDomainName: 255 octets, 126 pointers) -----
 struct NameWalk {
     const uint8_t *m; uint32_t mlen, p, wire, after; int ptrs; bool jumped;
