@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t bswap16(uint32_t v) { return __byte_perm(v, 
 // ------------------------------------------------------------------------------------------------
 struct Tabs {
     const uint2    *ep;    uint32_t ep_mask, ep_shift;
-    const uint32_t *soa;   uint32_t soa_stride;
+    const uint4    *rowq;                      // 3 x 16 B per endpoint row (dev_tables.h RowQ)
     const uint4    *dns;   uint32_t dns_shift;
     const uint4    *route; uint32_t route_shift;
     const uint32_t *pre;                       // CIDR /16 prefilter (null when there are no CIDR rules)
@@ -87,43 +87,41 @@ struct Tabs {
 #define CLAWKER_MARK_ 0xC1A4u          // common.h:73
 #define DOCKER_DNS_NBO 0x0b00007fu     // bpf_htonl(0x7f00000b), common.h:62
 
-// dns_cache[ip] -> domain_hash.  One 16 B bucket load; second bucket only when the first is full.
+// dns_cache[ip] -> domain_hash.  One 16 B bucket load; the second bucket is read only when the first is
+// full (slot 1 occupied) and missed.  The key 0xffffffff never enters the table (it is the empty marker):
+// the host keeps that one row out of band (dns_ffff_*).
 __device__ __forceinline__ bool dns_lookup(const DevTables &T, const Tabs &tb, uint32_t ip, uint32_t &hash)
 {
-    bool hit = false;
-    if (tb.dns) {
-        uint4 v = tb.dns[hash_a(ip) >> tb.dns_shift];
-        bool e0 = (v.x & v.y) == 0xffffffffu, e1 = (v.z & v.w) == 0xffffffffu;
-        if (v.x == ip && !e0) { hash = v.y; hit = true; }
-        else if (v.z == ip && !e1) { hash = v.w; hit = true; }
-        else if (!e0 && !e1) {
-            v = tb.dns[hash_b(ip) >> tb.dns_shift];
-            e0 = (v.x & v.y) == 0xffffffffu; e1 = (v.z & v.w) == 0xffffffffu;
-            if (v.x == ip && !e0) { hash = v.y; hit = true; }
-            else if (v.z == ip && !e1) { hash = v.w; hit = true; }
-        }
-    }
-    if (!hit && ip == 0xffffffffu && T.dns_ffff_present) { hash = T.dns_ffff_hash; hit = true; }
-    return hit;
+    if (ip == 0xffffffffu) { hash = T.dns_ffff_hash; return T.dns_ffff_present != 0; }
+    if (!tb.dns) return false;
+    uint4 v = tb.dns[hash_a(ip) >> tb.dns_shift];
+    if (v.x == ip) { hash = v.y; return true; }
+    if (v.z == ip) { hash = v.w; return true; }
+    if (v.z == 0xffffffffu) return false;
+    v = tb.dns[hash_b(ip) >> tb.dns_shift];
+    if (v.x == ip) { hash = v.y; return true; }
+    if (v.z == ip) { hash = v.w; return true; }
+    return false;
 }
 
-// route_map[{hash, port}] -> envoy_port
+// route_map[{hash, port}] -> envoy_port.  Slot (lo, hi): hi = domain_hash, lo = dst_port << 16 | envoy_port;
+// empty = ~0 (the host rejects the one route whose key and value are all ones).
 __device__ __forceinline__ bool route_lookup(const Tabs &tb, uint32_t hash, uint32_t port, uint32_t &eport)
 {
     if (!tb.route) return false;
-    const uint32_t f = route_fold(hash, port), klo = port << 16;
+    const uint32_t f = route_fold(hash, port);
     uint4 v = tb.route[hash_a(f) >> tb.route_shift];
-    bool e0 = (v.x & v.y) == 0xffffffffu, e1 = (v.z & v.w) == 0xffffffffu;
-    // slot (lo, hi): hi = hash, lo = port << 16 | envoy_port
-    if (v.y == hash && (v.x & 0xffff0000u) == klo && !e0) { eport = v.x & 0xffffu; return true; }
-    if (v.w == hash && (v.z & 0xffff0000u) == klo && !e1) { eport = v.z & 0xffffu; return true; }
-    if (!e0 && !e1) {
+    uint32_t lo = 0xffffffffu;
+    if (v.y == hash && (v.x >> 16) == port) lo = v.x;
+    else if (v.w == hash && (v.z >> 16) == port) lo = v.z;
+    else if ((v.z & v.w) != 0xffffffffu) {
         v = tb.route[hash_b(f) >> tb.route_shift];
-        e0 = (v.x & v.y) == 0xffffffffu; e1 = (v.z & v.w) == 0xffffffffu;
-        if (v.y == hash && (v.x & 0xffff0000u) == klo && !e0) { eport = v.x & 0xffffu; return true; }
-        if (v.w == hash && (v.z & 0xffff0000u) == klo && !e1) { eport = v.z & 0xffffu; return true; }
+        if (v.y == hash && (v.x >> 16) == port) lo = v.x;
+        else if (v.w == hash && (v.z >> 16) == port) lo = v.z;
     }
-    return false;
+    if (lo == 0xffffffffu) return false;           // miss, or an empty slot "matching" {0xffffffff, 65535}
+    eport = lo & 0xffffu;
+    return true;
 }
 
 // A12: dst inside any allowed CIDR.  2-bit /24 directory + 256-bit leaf bitmaps, both L2-resident.
@@ -288,7 +286,8 @@ __device__ __forceinline__ uint32_t make_word(const Decision &d, const clk_conta
 
 __device__ __forceinline__ uint32_t mhash(unsigned long long key)
 {
-    return (uint32_t)(((key ^ (key >> 29)) * 0x9E3779B97F4A7C15ull) >> 32);
+    uint32_t t = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u);
+    return t ^ (t >> 15);
 }
 
 __device__ __forceinline__ void metric_global_add(const DevTables &T, unsigned long long key, unsigned long long cnt)
@@ -505,7 +504,7 @@ __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, 
     ag.counts = (unsigned int *)(smem + L.agg_counts);
     for (uint32_t i = threadIdx.x; i < MSLOTS; i += blockDim.x) { ag.keys[i] = 0ull; ag.counts[i] = 0u; }
     uint64_t *bars = (uint64_t *)(smem + L.bars);
-    tb.ep = T.ep_slots; tb.ep_mask = T.ep_mask; tb.ep_shift = T.ep_shift; tb.soa = T.ep_soa; tb.soa_stride = T.soa_stride;
+    tb.ep = T.ep_slots; tb.ep_mask = T.ep_mask; tb.ep_shift = T.ep_shift; tb.rowq = T.ep_rowq;
     tb.dns = T.dns_b; tb.dns_shift = T.dns_shift; tb.route = T.route_b; tb.route_shift = T.route_shift; tb.pre = T.cidr_pre;
     const uint32_t nb = T.stage_ep_bytes + T.stage_soa_bytes + T.stage_dns_bytes + T.stage_route_bytes + T.stage_pre_bytes;
     if (threadIdx.x == 0) { for (uint32_t i = 0; i <= n_bars; i++) mbar_init(&bars[i], 1); fence_mbar_init(); }
@@ -514,14 +513,14 @@ __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, 
         if (threadIdx.x == 0) {
             mbar_expect_tx(&bars[n_bars], nb);
             if (T.stage_ep_bytes)    tma_load_1d(smem + L.ep, T.ep_slots, T.stage_ep_bytes, &bars[n_bars]);
-            if (T.stage_soa_bytes)   tma_load_1d(smem + L.soa, T.ep_soa, T.stage_soa_bytes, &bars[n_bars]);
+            if (T.stage_soa_bytes)   tma_load_1d(smem + L.soa, T.ep_rowq, T.stage_soa_bytes, &bars[n_bars]);
             if (T.stage_dns_bytes)   tma_load_1d(smem + L.dns, T.dns_b, T.stage_dns_bytes, &bars[n_bars]);
             if (T.stage_route_bytes) tma_load_1d(smem + L.route, T.route_b, T.stage_route_bytes, &bars[n_bars]);
             if (T.stage_pre_bytes)   tma_load_1d(smem + L.pre, T.cidr_pre, T.stage_pre_bytes, &bars[n_bars]);
         }
         mbar_wait(&bars[n_bars], 0);
         if (T.stage_ep_bytes)    tb.ep = (const uint2 *)(smem + L.ep);
-        if (T.stage_soa_bytes)   tb.soa = (const uint32_t *)(smem + L.soa);
+        if (T.stage_soa_bytes)   tb.rowq = (const uint4 *)(smem + L.soa);
         if (T.stage_dns_bytes)   tb.dns = (const uint4 *)(smem + L.dns);
         if (T.stage_route_bytes) tb.route = (const uint4 *)(smem + L.route);
         if (T.stage_pre_bytes)   tb.pre = (const uint32_t *)(smem + L.pre);
@@ -553,12 +552,11 @@ __device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb
     word = 0; hm = false; mk = 0;
     if (r < 0) return true;                                                      // no endpoint: no socket event
 
-    const uint32_t S = tb.soa_stride;
-    const uint32_t *so = tb.soa + r;
-    const uint32_t uid = so[SOA_UID * S], mark = so[SOA_MARK * S], fl = so[SOA_FLAGS * S];
-    const uint32_t envoy = so[SOA_ENVOY * S], coredns = so[SOA_COREDNS * S], gateway = so[SOA_GATEWAY * S];
-    const uint32_t net = so[SOA_NET * S], mask = so[SOA_MASK * S], hp_ip = so[SOA_HPIP * S], ports = so[SOA_PORTS * S];
-    const uint32_t hp_port = ports & 0xffffu, egress_port = ports >> 16;
+    const uint4 *rq = tb.rowq + 3 * r;
+    const uint4 ra = rq[0], rb = rq[1], rc = rq[2];
+    const uint32_t uid = ra.x, mark = ra.y, fl = ra.z, crow = ra.w;
+    const uint32_t envoy = rb.x, coredns = rb.y, gateway = rb.z, hp_ip = rb.w;
+    const uint32_t net = rc.x, mask = rc.y, hp_port = rc.z & 0xffffu, egress_port = rc.z >> 16;
 
     const uint32_t ip = ingress ? src : dst, port = raw ? 0u : (ingress ? sport : dport);
     const uint32_t hook = tcp ? CLK_HOOK_CONNECT4 : udp ? (ingress ? CLK_HOOK_RECVMSG4 : CLK_HOOK_SENDMSG4) : CLK_HOOK_SOCK_CREATE;
@@ -597,7 +595,7 @@ __device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb
         w |= (nport & 0xffffu) << 8;
     }
     word = w;
-    if (metric) { hm = true; mk = ((unsigned long long)((mp & 0xffffu) | (so[SOA_CROW * S] << 16) | (metric << 30)) << 32) | mh; }   // == metric_pack
+    if (metric) { hm = true; mk = ((unsigned long long)((mp & 0xffffu) | (crow << 16) | (metric << 30)) << 32) | mh; }   // == metric_pack
     return true;
 }
 
@@ -619,21 +617,21 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
     uint64_t *bars = (uint64_t *)(smem + L.bars) + warp * kStages;
     uint8_t *tiles = smem + L.tiles + warp * (kStages * WTILE_BYTES);
     uint32_t *queue = (uint32_t *)(smem + L.queue) + warp * WQ_CAP;
-    const unsigned long long n_tiles = (n + 31ull) >> 5;
-    const unsigned long long gw = (unsigned long long)blockIdx.x * FAST_WARPS + warp, W = (unsigned long long)gridDim.x * FAST_WARPS;
+    const uint32_t n_tiles = (uint32_t)((n + 31ull) >> 5);   // n < 2^31 on this path
+    const uint32_t gw = blockIdx.x * FAST_WARPS + warp, W = gridDim.x * FAST_WARPS;
     const bool do_metrics = !(flags & CLK_F_NO_METRICS);
     const uint32_t gflags = flags & ~CLK_F_NAME_STAGE;
     __syncthreads();                                         // tables staged, aggregation table zeroed, barriers initialised
 
     if (lane == 0) {
         for (int s = 0; s < kStages; s++) {
-            unsigned long long t = gw + (unsigned long long)s * W;
+            uint32_t t = gw + (uint32_t)s * W;
             if (t < n_tiles) { mbar_expect_tx(&bars[s], WTILE_BYTES); tma_load_2d(tiles + s * WTILE_BYTES, &map, &bars[s], 0, (int)(t << 5)); }
         }
     }
     uint32_t qn = 0;                                         // entries in this warp's queue (warp-uniform)
     uint32_t it = 0;
-    for (unsigned long long t = gw; t < n_tiles; t += W, it++) {
+    for (uint32_t t = gw; t < n_tiles; t += W, it++) {
         const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
         mbar_wait(&bars[s], ph);
         const uint8_t *slot = tiles + s * WTILE_BYTES + lane * 64;
@@ -643,10 +641,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
         const uint2 q2 = *(const uint2 *)(slot + ((2u ^ x) << 4));
         __syncwarp();                                                        // every lane holds its header words
         if (lane == 0) {
-            unsigned long long tn = t + (unsigned long long)kStages * W;
+            uint32_t tn = t + (uint32_t)kStages * W;
             if (tn < n_tiles) { fence_proxy_async(); mbar_expect_tx(&bars[s], WTILE_BYTES); tma_load_2d(tiles + s * WTILE_BYTES, &map, &bars[s], 0, (int)(tn << 5)); }
         }
-        const unsigned long long i = (t << 5) + lane;
+        const uint32_t i = (t << 5) + lane;
         bool hm = false, slow = false; unsigned long long mk = 0; uint32_t w = 0;
         if (i < n) {
             slow = !fast_classify(T, tb, w3, q1, q2.x, q2.y, w, hm, mk);
@@ -654,7 +652,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
         }
         const unsigned sm = __ballot_sync(0xffffffffu, slow);
         if (sm) {
-            if (slow) queue[qn + __popc(sm & ((1u << lane) - 1u))] = (uint32_t)i;
+            if (slow) queue[qn + __popc(sm & ((1u << lane) - 1u))] = i;
             qn += __popc(sm);
             __syncwarp();
         }

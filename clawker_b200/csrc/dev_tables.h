@@ -111,7 +111,7 @@ CLK_HD uint64_t metric_pack(uint32_t hash, uint32_t port, uint32_t crow, uint32_
 struct DevTables {
     const EpRow    *ep_rows;     uint32_t n_ep_rows;
     const uint2    *ep_slots;    uint32_t ep_mask, ep_shift;   // slot: {ip, EpRow index + 1} (y == 0 empty), index hash_a(ip) >> ep_shift, load <= 1/4
-    const uint32_t *ep_soa;      uint32_t soa_stride;    // SOA_FIELDS arrays of soa_stride words, indexed by EpRow index
+    const uint4    *ep_rowq;                             // 3 x uint4 per EpRow index: {uid,mark,flags,crow} {envoy,coredns,gateway,hp_ip} {net,mask,hp_port|egress<<16,0}
     const Ep6Key   *ep6;         uint32_t n_ep6;         // linear (<= 256 rows), rarely non-empty
     const ContRow  *crows;       uint32_t n_crows;
     const uint32_t *cg_slots;    uint32_t cg_mask;       // slot: ContRow index + 1, keyed by mix64(cgroup_id)

@@ -87,11 +87,12 @@ struct clk_engine {
     // device
     Snapshot snap[2]; int active = 0; bool published = false;
     DevTables T;                                                         // active snapshot
-    DevBuf m_keys, m_counts, m_dropped;
+    DevBuf m_keys, m_counts, m_dropped;      // this GPU's metrics_map (kernels write)
+    DevBuf g_keys, g_counts, g_dropped;      // merged view after the all-gather (clk_counters_import)
     DevBuf work_pkts[3], work_offs[3], work_verd[3], scan_sums, scan_pos, scan_total, upd_out, ctr_block;
     clk_stats stats;
     int loader = LOADER_TMA_SW64;
-    int stages = 3;
+    int stages = 1;
     bool stage_tables = true;
     uint64_t chunk_pkts = 1u << 21;
 
@@ -257,7 +258,7 @@ int publish_locked(clk_engine *e)
         std::vector<std::pair<uint64_t, std::pair<uint32_t, uint32_t>>> items;
         for (auto &kv : e->dns) {
             uint64_t s = (uint64_t)kv.first | ((uint64_t)kv.second.domain_hash << 32);
-            if (s == SLOT_EMPTY) { T.dns_ffff_present = 1; T.dns_ffff_hash = 0xffffffffu; continue; }
+            if (kv.first == 0xffffffffu) { T.dns_ffff_present = 1; T.dns_ffff_hash = kv.second.domain_hash; continue; }
             items.push_back({ s, { hash_a(kv.first), hash_b(kv.first) } });
         }
         if (!items.empty()) build_buckets(dns_b, items);
@@ -318,20 +319,16 @@ int publish_locked(clk_engine *e)
     }
     // ---- upload -------------------------------------------------------------------------------------
     CUDA_TRY(e, upload(S.crows, crows, st));       CUDA_TRY(e, upload(S.cg_slots, cg_slots, st));
-    // structure-of-arrays copy of the endpoint rows (dev_tables.h SOA_*), at least one zero row
-    const uint32_t soa_stride = (uint32_t)((std::max<size_t>(rows.size(), 1) + 3) & ~(size_t)3);
-    std::vector<uint32_t> soa((size_t)SOA_FIELDS * soa_stride, 0);
+    // the fields the fast path needs, packed as three 16-byte words per row (48 B stride: conflict-free LDS.128 for 8 rows)
+    std::vector<uint4> rowq(std::max<size_t>(rows.size(), 1) * 3, uint4{ 0, 0, 0, 0 });
     for (size_t i = 0; i < rows.size(); i++) {
         const EpRow &r = rows[i];
-        soa[SOA_UID * soa_stride + i] = r.uid; soa[SOA_MARK * soa_stride + i] = r.so_mark; soa[SOA_FLAGS * soa_stride + i] = r.flags;
-        soa[SOA_ENVOY * soa_stride + i] = r.cfg.envoy_ip; soa[SOA_COREDNS * soa_stride + i] = r.cfg.coredns_ip;
-        soa[SOA_GATEWAY * soa_stride + i] = r.cfg.gateway_ip; soa[SOA_NET * soa_stride + i] = r.cfg.net_addr;
-        soa[SOA_MASK * soa_stride + i] = r.cfg.net_mask; soa[SOA_HPIP * soa_stride + i] = r.cfg.host_proxy_ip;
-        soa[SOA_PORTS * soa_stride + i] = (uint32_t)r.cfg.host_proxy_port | ((uint32_t)r.cfg.egress_port << 16);
-        soa[SOA_CROW * soa_stride + i] = r.crow;
+        rowq[3 * i + 0] = uint4{ r.uid, r.so_mark, r.flags, r.crow };
+        rowq[3 * i + 1] = uint4{ r.cfg.envoy_ip, r.cfg.coredns_ip, r.cfg.gateway_ip, r.cfg.host_proxy_ip };
+        rowq[3 * i + 2] = uint4{ r.cfg.net_addr, r.cfg.net_mask, (uint32_t)r.cfg.host_proxy_port | ((uint32_t)r.cfg.egress_port << 16), 0 };
     }
     CUDA_TRY(e, upload(S.ep_rows, rows, st));      CUDA_TRY(e, upload(S.ep_slots, ep_slots, st));
-    CUDA_TRY(e, upload(S.ep_soa, soa, st));        CUDA_TRY(e, upload(S.ep6, ep6, st));
+    CUDA_TRY(e, upload(S.ep_soa, rowq, st));       CUDA_TRY(e, upload(S.ep6, ep6, st));
     CUDA_TRY(e, upload(S.dns, dns_b, st));         CUDA_TRY(e, upload(S.route, route_b, st));
     CUDA_TRY(e, upload(S.cidr_pre, pre, st));
     CUDA_TRY(e, upload(S.cidr_l1, l1, st));        CUDA_TRY(e, upload(S.cidr_l2_keys, l2_keys, st));
@@ -342,7 +339,7 @@ int publish_locked(clk_engine *e)
 
     T.ep_rows = rows.empty() ? nullptr : (const EpRow *)S.ep_rows.p; T.n_ep_rows = (uint32_t)rows.size();
     if (n_ep4) { T.ep_slots = (const uint2 *)S.ep_slots.p; T.ep_mask = (uint32_t)ep_slots.size() - 1; T.ep_shift = shift_for((uint32_t)ep_slots.size()); }
-    T.ep_soa = (const uint32_t *)S.ep_soa.p; T.soa_stride = soa_stride;
+    T.ep_rowq = (const uint4 *)S.ep_soa.p;
     T.ep6 = ep6.empty() ? nullptr : (const Ep6Key *)S.ep6.p; T.n_ep6 = (uint32_t)ep6.size();
     T.crows = crows.empty() ? nullptr : (const ContRow *)S.crows.p; T.n_crows = (uint32_t)crows.size();
     T.cg_slots = (const uint32_t *)S.cg_slots.p; T.cg_mask = (uint32_t)cg_slots.size() - 1;
@@ -364,7 +361,7 @@ int publish_locked(clk_engine *e)
     T.m_mask = e->T.m_mask; T.m_dropped = (unsigned long long *)e->m_dropped.p;
     // shared-memory staging budget: endpoints <= 256 rows, dns <= 32 KiB, route <= 8 KiB
     if (e->stage_tables) {
-        if (n_ep4 && rows.size() <= 256) { T.stage_ep_bytes = (uint32_t)ep_slots.size() * 8; T.stage_soa_bytes = (uint32_t)soa.size() * 4; }
+        if (n_ep4 && rows.size() <= 256) { T.stage_ep_bytes = (uint32_t)ep_slots.size() * 8; T.stage_soa_bytes = (uint32_t)rowq.size() * 16; }
         if (!dns_b.empty() && dns_b.size() * 16 <= 32768) T.stage_dns_bytes = (uint32_t)dns_b.size() * 16;
         if (!route_b.empty() && route_b.size() * 16 <= 8192) T.stage_route_bytes = (uint32_t)route_b.size() * 16;
         if (n_cidr) T.stage_pre_bytes = 8192;
@@ -451,7 +448,7 @@ void clk_engine_destroy(clk_engine *e)
         cudaSetDevice(e->device);
         cudaDeviceSynchronize();
         e->snap[0].release(); e->snap[1].release();
-        for (DevBuf *b : { &e->m_keys, &e->m_counts, &e->m_dropped, &e->scan_sums, &e->scan_pos, &e->scan_total, &e->upd_out, &e->ctr_block }) b->release();
+        for (DevBuf *b : { &e->m_keys, &e->m_counts, &e->m_dropped, &e->g_keys, &e->g_counts, &e->g_dropped, &e->scan_sums, &e->scan_pos, &e->scan_total, &e->upd_out, &e->ctr_block }) b->release();
         for (int i = 0; i < 3; i++) { e->work_pkts[i].release(); e->work_offs[i].release(); e->work_verd[i].release(); if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]); }
         if (e->ev0) cudaEventDestroy(e->ev0);
         if (e->ev1) cudaEventDestroy(e->ev1);
@@ -821,6 +818,13 @@ int clk_counters_export(clk_engine *e, void *d_block, void *stream)
     return CLK_OK;
 }
 
+static DevTables global_view(clk_engine *e)
+{
+    DevTables G = e->T;
+    G.m_keys = (unsigned long long *)e->g_keys.p; G.m_counts = (unsigned long long *)e->g_counts.p; G.m_dropped = (unsigned long long *)e->g_dropped.p;
+    return G;
+}
+
 int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, void *stream)
 {
     if (!e || !d_blocks) return fail(e, CLK_EINVAL, "NULL");
@@ -828,35 +832,43 @@ int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, 
     std::lock_guard<std::mutex> g(e->mu);
     int rc = ensure_published(e); if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    const char *err = launch_counters_clear(e->T, st);
-    if (!err) err = launch_counters_import(e->T, (const clk_metric *)d_blocks, (unsigned long long)n_blocks * (e->T.m_mask + 1), st);
+    const size_t slots = (size_t)e->T.m_mask + 1;
+    CUDA_TRY(e, e->g_keys.ensure(slots * 8)); CUDA_TRY(e, e->g_counts.ensure(slots * 8)); CUDA_TRY(e, e->g_dropped.ensure(8));
+    DevTables G = global_view(e);
+    const char *err = launch_counters_clear(G, st);
+    if (!err) err = launch_counters_import(G, (const clk_metric *)d_blocks, (unsigned long long)n_blocks * slots, st);
     if (err) return fail(e, CLK_EIO, "counters import: %s", err);
     e->stats.kernel_launches += 2;
     return CLK_OK;
 }
 
-int clk_counters_read(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n)
+static int counters_read_impl(clk_engine *e, bool global, clk_metric *out, uint32_t cap, uint32_t *n)
 {
     if (!e || !n) return fail(e, CLK_EINVAL, "NULL");
     NEED_GPU(e);
     std::lock_guard<std::mutex> g(e->mu);
     int rc = ensure_published(e); if (rc) return rc;
+    if (global && !e->g_keys.p) { *n = 0; return CLK_OK; }
     CUDA_TRY(e, cudaSetDevice(e->device));
     CUDA_TRY(e, cudaDeviceSynchronize());
     uint32_t rows = e->T.m_mask + 1;
     CUDA_TRY(e, e->ctr_block.ensure((size_t)rows * sizeof(clk_metric)));
-    const char *err = launch_counters_export(e->T, (clk_metric *)e->ctr_block.p, e->stream);
+    DevTables V = global ? global_view(e) : e->T;
+    const char *err = launch_counters_export(V, (clk_metric *)e->ctr_block.p, e->stream);
     if (err) return fail(e, CLK_EIO, "counters export: %s", err);
     e->stats.kernel_launches++;
     std::vector<clk_metric> host(rows);
     CUDA_TRY(e, cudaMemcpyAsync(host.data(), e->ctr_block.p, (size_t)rows * sizeof(clk_metric), cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(&e->stats.metrics_dropped, e->m_dropped.p, 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(&e->stats.metrics_dropped, V.m_dropped, 8, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     uint32_t k = 0;
     for (auto &m : host) if (m.count) { if (out && k < cap) out[k] = m; k++; }
     *n = k;
     return CLK_OK;
 }
+
+int clk_counters_read(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n) { return counters_read_impl(e, false, out, cap, n); }
+int clk_counters_read_global(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n) { return counters_read_impl(e, true, out, cap, n); }
 
 int clk_counters_reset(clk_engine *e)
 {

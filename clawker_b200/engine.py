@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
         "clk_classify_events": (i32, [vp, vp, u64, u32, vp]),
         "clk_dns_answers": (i32, [vp, vp, vp, u64, vp, vp, u64, C.POINTER(u64), i32, u32]),
         "clk_counters_read": (i32, [vp, vp, u32, C.POINTER(u32)]),
+        "clk_counters_read_global": (i32, [vp, vp, u32, C.POINTER(u32)]),
         "clk_counters_reset": (i32, [vp]),
         "clk_counters_block_rows": (i32, [vp, C.POINTER(u32)]),
         "clk_counters_export": (i32, [vp, vp, vp]),
@@ -99,7 +100,7 @@ EXPORTS = ["clk_abi_version", "clk_strerror", "clk_last_error", "clk_engine_crea
            "clk_dns_update", "clk_dns_gc", "clk_validate_dst", "clk_domain_hash", "clk_ip_to_u32",
            "clk_cidr_to_addr_mask", "clk_rules_compile", "clk_rules_dump", "clk_publish", "clk_classify_slots",
            "clk_classify_varlen", "clk_classify_slots_dev", "clk_classify_varlen_dev", "clk_classify_events",
-           "clk_dns_answers", "clk_counters_read", "clk_counters_reset", "clk_counters_block_rows",
+           "clk_dns_answers", "clk_counters_read", "clk_counters_read_global", "clk_counters_reset", "clk_counters_block_rows",
            "clk_counters_export", "clk_counters_import", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
 
 
@@ -275,12 +276,14 @@ class Engine:
         return out[:k.value]
 
     # ---- counters -----------------------------------------------------------------------------------
-    def counters(self) -> np.ndarray:
+    def counters(self, merged: bool = False) -> np.ndarray:
+        """metrics_map rows: this GPU's table, or (merged=True) the all-rank view of the last counters_import."""
+        fn = self.L.clk_counters_read_global if merged else self.L.clk_counters_read
         n = C.c_uint32()
-        self._ck(self.L.clk_counters_read(self.h, None, 0, C.byref(n)))
+        self._ck(fn(self.h, None, 0, C.byref(n)))
         out = np.zeros(n.value, dtype=METRIC_DTYPE)
         if n.value:
-            self._ck(self.L.clk_counters_read(self.h, out.ctypes.data, n.value, C.byref(n)))
+            self._ck(fn(self.h, out.ctypes.data, n.value, C.byref(n)))
         return out
 
     def counters_reset(self):

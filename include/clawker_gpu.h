@@ -326,9 +326,12 @@ int clk_counters_reset(clk_engine *e);
 /* Fixed-size device block for the one collective of the multi-GPU path: the engine's
  * metric table exported as `rows` x 24 B (clk_metric, count==0 rows are empty) into a
  * caller-provided DEVICE buffer; after the caller's ncclAllGather of these blocks,
- * clk_counters_import merges `n_blocks` gathered blocks (device pointer) into the local
- * table, replacing it — every rank ends with the same summed view. */
+ * clk_counters_import sums `n_blocks` gathered blocks (device pointer) into the engine's
+ * merged-view table (the local per-GPU table keeps counting on its own) — every rank ends
+ * with the same summed view, which is what summing the reference's PERCPU values yields. */
 int clk_counters_block_rows(clk_engine *e, uint32_t *rows);
+/* The merged (all ranks) view written by the last clk_counters_import; same shape as clk_counters_read. */
+int clk_counters_read_global(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n);
 int clk_counters_export(clk_engine *e, void *d_block, void *stream);
 int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, void *stream);
 
