@@ -1,0 +1,59 @@
+"""Two-GPU form of the sharding test (runs only where >= 2 CUDA devices are visible, e.g. gpurun --gpus 2):
+packet shards on two B200s, ncclAllGather of the counter blocks, merged view == oracle on the whole batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N = 400_003
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from clawker_b200 import capture, sharding
+    from util import make_engine
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    w = capture.make_workload("c2")
+    pk = capture.gen_slots(w, N, seed=4)
+    lo, hi = sharding.shard_range(N, rank, world)
+    e = make_engine(w, device=rank, max_metrics=1 << 18)
+    verd = e.classify_slots(pk[lo:hi])
+    sharding.allgather_counters(e)
+    q.put((rank, lo, hi, verd, e.counters(merged=True), e.counters()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_shards_and_nccl_counter_allgather():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from clawker_b200 import capture
+    from oracle import oracle
+    from util import assert_same_metrics, oracle_tables
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    w = capture.make_workload("c2")
+    pk = capture.gen_slots(w, N, seed=4)
+    want_v, want_m = oracle.Oracle("port").load(oracle_tables(w)).classify(pk)
+    assert np.array_equal(np.concatenate([r[3] for r in res]), want_v)
+    for rank, lo, hi, verd, merged, local in res:
+        assert_same_metrics(merged, want_m, f"rank {rank} merged")
+        assert int(local["count"].sum()) < int(merged["count"].sum())

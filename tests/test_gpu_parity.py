@@ -87,3 +87,68 @@ def test_varlen_name_stage():
     # sanity: the capture really exercises every stage
     f = abi.verdict_fields(got)
     assert (f["name"] == 1).sum() > 100 and (f["name"] == 2).sum() > 100 and f["nupd"].sum() > 100
+
+
+def test_golden_reference_fixtures():
+    """Fixtures produced by the reference's own eBPF programs (tests/golden/make_golden.py)."""
+    from pathlib import Path
+    g = Path(__file__).resolve().parent / "golden"
+    w = capture.make_workload("c2")
+    z = np.load(g / "events_ref.npz")
+    e = make_engine(w, with_cidrs=False)
+    assert_same_verdicts(e.classify_events(z["events"]), z["verdicts"], "golden events")
+    assert_same_metrics(e.counters(), z["metrics"], "golden events")
+    z = np.load(g / "packets_ref.npz")
+    e = make_engine(w, with_cidrs=False)
+    assert_same_verdicts(e.classify_slots(z["packets"]), z["verdicts"], "golden packets")
+    assert_same_metrics(e.counters(), z["metrics"], "golden packets")
+
+
+def test_table_updates_take_effect_after_publish():
+    """Epoch semantics: map ops are invisible until clk_publish, then every packet sees the new snapshot."""
+    import ctypes as C
+    w = capture.make_workload("c1")
+    pk = capture.gen_slots(w, 5000, seed=8)
+    e = make_engine(w)
+    before = e.classify_slots(pk)
+    cg = next(iter(w.tables["containers"]))
+    e.map_update(abi.MAP_BYPASS, C.c_uint64(cg), C.c_uint8(1))
+    e.publish()
+    after = e.classify_slots(pk)
+    t = oracle_tables(w)
+    t["bypass"] = {cg: 1}
+    want, _ = oracle.Oracle("port").load(t).classify(pk)
+    assert_same_verdicts(after, want, "after bypass")
+    assert (before != after).any() and (abi.verdict_fields(after)["metric"] == 3).any()
+    e.map_delete(abi.MAP_BYPASS, C.c_uint64(cg))
+    e.publish()
+    assert_same_verdicts(e.classify_slots(pk), before, "after unbypass")
+
+
+def test_large_tables_sweep():
+    """BASELINE config 5 shape at test scale: rule-table sizes 16 .. 64k, tables too large for shared memory."""
+    for n_rules in (16, 4096, 65536):
+        w = capture.make_workload("c5:%d" % n_rules)
+        pk = capture.gen_slots(w, 100_000, seed=n_rules)
+        want, wm = oracle.Oracle("port").load(oracle_tables(w)).classify(pk)
+        e = make_engine(w)
+        assert_same_verdicts(e.classify_slots(pk), want, f"c5:{n_rules}")
+        assert_same_metrics(e.counters(), wm, f"c5:{n_rules}")
+
+
+def test_full_size_properties():
+    """10 M packets (BASELINE configs[1] full size): properties that do not need the oracle at full size —
+    a permutation of the packets permutes the verdicts, and metric counts sum to the number of metric-emitting verdicts."""
+    w = capture.make_workload("c2")
+    base = capture.gen_slots(w, 500_000, seed=42)
+    pk = np.tile(base, (20, 1))
+    e = make_engine(w)
+    v = e.classify_slots(pk)
+    assert np.array_equal(v.reshape(20, -1), np.tile(v[:500_000], (20, 1)))                 # same packet, same verdict, anywhere in the batch
+    want, _ = oracle.Oracle("port").load(oracle_tables(w)).classify(base)
+    assert_same_verdicts(v[:500_000], want, "first 500k of the 10M batch")
+    m = e.counters()
+    assert int(m["count"].sum()) == int((abi.verdict_fields(v)["metric"] != 0).sum())
+    perm = np.random.Generator(np.random.PCG64(1)).permutation(pk.shape[0])[:1_000_000]
+    e2 = make_engine(w)
+    assert np.array_equal(e2.classify_slots(pk[perm]), v[perm])

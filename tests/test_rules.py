@@ -1,0 +1,165 @@
+"""The rule compiler against the reference's own unit-test vectors (tests/golden/reference_vectors.py):
+once for the oracle's Python restatement, once for the product's C++ compiler behind the C-ABI."""
+import pytest
+
+from clawker_b200 import dnsbpf, ebpf, engine, firewall
+from oracle import rules_oracle as ro
+
+from golden import reference_vectors as V
+
+
+def R(t):
+    return ro.EgressRule(*t)
+
+
+# ---- oracle restatement ------------------------------------------------------------------------------
+@pytest.mark.parametrize("dst,want_err", V.VALIDATE_DST)
+def test_oracle_validate_dst(dst, want_err):
+    assert ro.validate_dst(dst) == (not want_err)
+
+
+@pytest.mark.parametrize("name,rules,want", V.TCP_MAPPINGS)
+def test_oracle_tcp_mappings(name, rules, want):
+    assert ro.tcp_mappings([R(r) for r in rules], 10001) == want
+
+
+def test_oracle_corefile_zones():
+    assert ro.corefile_zones([R(r) for r in V.COREFILE_RULES]) == V.COREFILE_ZONES
+    z = ro.corefile_zones([R(r) for r in V.COREFILE_WILDCARD_RULES])
+    assert z[:2] == V.COREFILE_WILDCARD_ZONES_PREFIX and ".datadoghq.com" not in z
+
+
+def test_oracle_server_names_http_domains():
+    for dst, exact, want in V.SERVER_NAMES:
+        assert ro.server_names(dst, set(exact)) == want
+    for dst, exact, want in V.HTTP_DOMAINS:
+        assert ro.http_domains(dst, set(exact)) == want
+
+
+def test_oracle_normalize_and_dedup():
+    for rules, want, warns in V.NORMALIZE_DEDUP:
+        out, w = ro.normalize_and_dedup([R(r) for r in rules])
+        assert [(r.dst, r.port) for r in out] == want and w == warns
+    for d, want in V.IS_WILDCARD:
+        assert ro.is_wildcard_domain(d) == want
+    for d, want in V.NORMALIZE_DOMAIN:
+        assert ro.normalize_domain(d) == want
+
+
+def test_oracle_domain_hash():
+    for variants, ref in V.DOMAIN_HASH_EQUAL:
+        assert {ro.domain_hash(v) for v in variants} == {ro.domain_hash(ref)}
+    for s, h in V.DOMAIN_HASH_KAT:
+        assert ro.domain_hash(s) == h
+    m = ro.tcp_mappings([R(V.WILDCARD_ROUTE_RULE)])
+    assert ro.domain_hash(m[0][0]) == ro.domain_hash(ro.normalize_domain(".example.com"))
+    for ip, want in V.IP_TO_U32:
+        assert ro.ip_to_u32(ip) == want
+
+
+# ---- product (C++ behind the C-ABI; host-only engine: no GPU needed for the control plane) ------------
+@pytest.fixture()
+def eng():
+    e = engine.Engine(host_only=True)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("dst,want_err", V.VALIDATE_DST)
+def test_product_validate_dst(dst, want_err):
+    assert engine.validate_dst(dst) == (not want_err)
+    if want_err:
+        with pytest.raises(ValueError):
+            firewall.ValidateDst(dst)
+    else:
+        firewall.ValidateDst(dst)
+
+
+@pytest.mark.parametrize("name,rules,want", V.TCP_MAPPINGS)
+def test_product_tcp_mappings(eng, name, rules, want):
+    c = firewall.compile_rules(eng, [firewall.EgressRule(*r) for r in rules])
+    assert c.tcp_mappings == want
+    # syncRoutes: route_map rows == {DomainHash(dst), port} -> envoy_port  (manager.go:1356-1377)
+    from clawker_b200 import abi
+    assert eng.map_count(abi.MAP_ROUTE) == len({(d, p) for d, p, _ in want})
+    for d, p, ep in want:
+        v = eng.map_lookup(abi.MAP_ROUTE, abi.RouteKey(ebpf.DomainHash(d), p, 0), abi.RouteVal())
+        assert v is not None and v.envoy_port == ep
+
+
+def test_product_corefile_zones(eng):
+    assert firewall.compile_rules(eng, [firewall.EgressRule(*r) for r in V.COREFILE_RULES]).zones == V.COREFILE_ZONES
+    z = firewall.compile_rules(eng, [firewall.EgressRule(*r) for r in V.COREFILE_WILDCARD_RULES]).zones
+    assert z[:2] == V.COREFILE_WILDCARD_ZONES_PREFIX and ".datadoghq.com" not in z
+
+
+def test_product_server_names(eng):
+    # serverNames() through the compiled SNI table: one tls rule per case (+ the exact sibling when given)
+    for dst, exact, want in V.SERVER_NAMES:
+        rules = [firewall.EgressRule(dst, "tls", 443, "allow")] + [firewall.EgressRule(x, "tls", 443, "allow") for x in exact]
+        got = firewall.compile_rules(eng, rules).server_names
+        assert got[:len(want)] == want and got[len(want):] == list(exact)
+
+
+def test_product_normalize_and_dedup(eng):
+    for rules, want, warns in V.NORMALIZE_DEDUP:
+        c = firewall.compile_rules(eng, [firewall.EgressRule(*r) for r in rules])
+        assert c.warnings == warns
+        # every surviving tls rule shows up as a zone (normalised, deduped)
+        zones = [z for z in c.zones if z not in ro.INTERNAL_HOSTS]
+        seen = []
+        for d, _ in want:
+            n = ro.normalize_domain(d)
+            if n not in seen:
+                seen.append(n)
+        assert zones == seen
+
+
+def test_product_domain_hash_and_addresses():
+    for variants, ref in V.DOMAIN_HASH_EQUAL:
+        assert {ebpf.DomainHash(v) for v in variants} == {ebpf.DomainHash(ref)}
+    for s, h in V.DOMAIN_HASH_KAT:
+        assert ebpf.DomainHash(s) == h
+    for ip, want in V.IP_TO_U32:
+        assert ebpf.IPToUint32(ip) == want
+    assert ebpf.Uint32ToIP(75059852) == "140.82.121.4"
+    assert ebpf.CIDRToAddrMask("172.20.0.0/16") == (ebpf.IPToUint32("172.20.0.0"), ebpf.IPToUint32("255.255.0.0"))
+    assert ebpf.CIDRToAddrMask("10.1.2.3/8")[0] == ebpf.IPToUint32("10.0.0.0")
+    with pytest.raises(ValueError):
+        ebpf.CIDRToAddrMask("10.0.0.0/33")
+
+
+def test_product_equals_oracle_on_synthetic_rule_sets(eng):
+    from clawker_b200 import capture
+    for cfg in ("c1", "c2", "c3"):
+        w = capture.make_workload(cfg, n_rules=600 if cfg == "c3" else None)
+        c = firewall.compile_rules(eng, w.rules)
+        o = ro.compile_rules(w.rules)
+        assert c.zones == o.zones and c.server_names == o.snis and c.tcp_mappings == o.mappings and c.warnings == o.warnings
+
+
+# ---- dnsbpf plugin surface ---------------------------------------------------------------------------
+class RecordingMap(dnsbpf.MapWriter):        # dnsbpf_test.go:31-58 recordingMap
+    def __init__(self):
+        self.entries = []
+
+    def Update(self, ip, domain_hash, ttl):
+        self.entries.append((ip, domain_hash, ttl))
+
+
+@pytest.mark.parametrize("zone,answers,want", V.SERVE_DNS)
+def test_dnsbpf_serve_dns(zone, answers, want):
+    types = {"A": dnsbpf.TYPE_A, "AAAA": dnsbpf.TYPE_AAAA}
+    msg = dnsbpf.Msg([dnsbpf.RR(n, types[t], ttl, rd if t == "A" else "") for n, t, ttl, rd in answers])
+    rec = RecordingMap()
+    h = dnsbpf.Handler(zone, rec, next_handler=lambda req: msg)
+    out = h.ServeDNS(object())
+    assert out is msg and len(out.answer) == len(answers)                 # response forwarded unchanged
+    assert rec.entries == [(ebpf.IPToUint32(ip), ebpf.DomainHash(hs), ttl) for ip, hs, ttl in want]
+    assert dnsbpf.Handler(zone, None, next_handler=lambda req: msg).ServeDNS(object()) is msg   # nil Map: skip writes
+
+
+def test_zone_to_domain():
+    for z, d in V.ZONE_TO_DOMAIN:
+        assert dnsbpf.zone_to_domain(z) == d
+    assert dnsbpf.Handler("x.", None).Name() == "dnsbpf"
