@@ -160,7 +160,9 @@ def run_gpu(args) -> None:
     del d_unique
     d_v = torch.empty(n, dtype=torch.int32, device=dev)
 
-    e = engine.Engine(device=local, max_metrics=1 << 19, max_dns_cache=1 << 21, max_routes=1 << 16)
+    # metrics_map max_entries: 8x the reference default (common.h:173) so every key of the synthetic capture is counted;
+    # keys beyond max_entries are dropped like the reference BPF_NOEXIST insert into a full map (--metrics-capacity)
+    e = engine.Engine(device=local, max_metrics=args.metrics_capacity, max_dns_cache=1 << 21, max_routes=1 << 16)
     e.load_tables(w.tables)
     e.compile_rules(w.rules)
     e.publish()
@@ -169,6 +171,7 @@ def run_gpu(args) -> None:
     d_gather = torch.empty(world * rows * 24, dtype=torch.uint8, device=dev) if world > 1 else None
 
     ts = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev)                           # the collective overlaps the next batch's kernel
     torch.cuda.set_stream(ts)
     st = ts.cuda_stream
     flags = 0
@@ -180,9 +183,11 @@ def run_gpu(args) -> None:
         if ev_pair:
             ev_pair[1].record(ts)
         if world > 1:                                              # the one collective: per-GPU counters over NVLink
-            e.counters_export(d_block.data_ptr(), st)
-            dist.all_gather_into_tensor(d_gather, d_block)
-            e.counters_import(d_gather.data_ptr(), world, st)
+            side.wait_stream(ts)
+            with torch.cuda.stream(side):
+                e.counters_export(d_block.data_ptr(), side.cuda_stream)
+                dist.all_gather_into_tensor(d_gather, d_block)
+                e.counters_import(d_gather.data_ptr(), world, side.cuda_stream)
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -199,6 +204,7 @@ def run_gpu(args) -> None:
     t0.record(ts)
     for k in range(args.steps):
         step(kern_events[k])
+    ts.wait_stream(side)
     t1.record(ts)
     torch.cuda.synchronize()
     if world > 1:
@@ -252,6 +258,7 @@ def run_gpu(args) -> None:
                     "d2h_bytes_per_step": n_e2e * 4, "packets_per_step": n_e2e, "ms_per_step": round(e2e_ms, 3),
                     "path": "clk_classify_slots (pinned host buffers, 3-stream chunked H2D/kernel/D2H)"},
             "gpu_launches": int(launches), "clocks": clocks,
+            "metrics": {"max_entries": args.metrics_capacity, "rows": int(e.counters().size), "dropped_increments": int(e.stats().metrics_dropped)},
         }
         if base:
             line["cpu_baseline"] = base
@@ -269,6 +276,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--packets", type=int, default=0, help="override packets per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--metrics-capacity", type=int, default=131072, help="metrics_map max_entries per GPU (reference: 16384; the synthetic capture produces ~76k distinct keys)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -290,28 +290,33 @@ __device__ __forceinline__ uint32_t mhash(unsigned long long key)
     return t ^ (t >> 15);
 }
 
-__device__ __forceinline__ void metric_global_add(const DevTables &T, unsigned long long key, unsigned long long cnt)
+// Returns the increments it had to drop (0 normally); callers accumulate them per thread and publish once.
+__device__ __forceinline__ unsigned long long metric_global_add(const DevTables &T, unsigned long long key, unsigned long long cnt)
 {
     uint32_t h = mhash(key) & T.m_mask;
     #pragma unroll 1
-    for (int p = 0; p < 128; p++) {
+    for (int p = 0; p < 64; p++) {
         unsigned long long cur = T.m_keys[h];
         if (cur != key) {
             if (cur != 0ull) { h = (h + 1) & T.m_mask; continue; }
+            // a new key: BPF_NOEXIST insert, refused once the map holds max_entries (metric_inc common.h:206-209)
+            const bool capped = T.m_max != 0xffffffffu;                 // the merged view (import) is uncapped and uncounted
+            if (capped && *(volatile unsigned long long *)&T.m_dropped[1] >= T.m_max) break;
             cur = atomicCAS(&T.m_keys[h], 0ull, key);
-            if (cur != 0ull && cur != key) { h = (h + 1) & T.m_mask; continue; }
+            if (cur == 0ull) { if (capped) atomicAdd(&T.m_dropped[1], 1ull); }
+            else if (cur != key) { h = (h + 1) & T.m_mask; continue; }
         }
         atomicAdd(&T.m_counts[h], cnt);
-        return;
+        return 0ull;
     }
-    atomicAdd(T.m_dropped, cnt);       // table full: the reference's BPF_NOEXIST insert fails the same way
+    return cnt;
 }
 
-struct MetricAgg { unsigned long long *keys; unsigned int *counts; };
+struct MetricAgg { unsigned long long *keys; unsigned int *counts; unsigned long long dropped; };
 
 // Two probes at most: keys that find a slot early (the frequent ones, by construction) stay in shared
 // memory for the CTA's lifetime; everything else goes straight to the device table.
-__device__ __forceinline__ void metric_cta_add(const DevTables &T, const MetricAgg &ag, unsigned long long key, unsigned int cnt)
+__device__ __forceinline__ void metric_cta_add(const DevTables &T, MetricAgg &ag, unsigned long long key, unsigned int cnt)
 {
     uint32_t h = mhash(key) & (MSLOTS - 1);
     #pragma unroll
@@ -321,11 +326,11 @@ __device__ __forceinline__ void metric_cta_add(const DevTables &T, const MetricA
         if (cur == 0ull || cur == key) { atomicAdd(&ag.counts[h], cnt); return; }
         h = (h + 1) & (MSLOTS - 1);
     }
-    metric_global_add(T, key, cnt);
+    ag.dropped += metric_global_add(T, key, cnt);
 }
 
 // All 32 lanes must call (tail lanes with has == false).
-__device__ __forceinline__ void metric_warp_emit(const DevTables &T, const MetricAgg &ag, bool has, unsigned long long key)
+__device__ __forceinline__ void metric_warp_emit(const DevTables &T, MetricAgg &ag, bool has, unsigned long long key)
 {
     unsigned m = __ballot_sync(0xffffffffu, has);
     if (has) {
@@ -334,11 +339,14 @@ __device__ __forceinline__ void metric_warp_emit(const DevTables &T, const Metri
     }
 }
 
-__device__ __forceinline__ void metric_cta_flush(const DevTables &T, const MetricAgg &ag)
+__device__ __forceinline__ void metric_cta_flush(const DevTables &T, MetricAgg &ag)
 {
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < MSLOTS; i += blockDim.x)
-        if (ag.keys[i]) metric_global_add(T, ag.keys[i], ag.counts[i]);
+        if (ag.keys[i]) ag.dropped += metric_global_add(T, ag.keys[i], ag.counts[i]);
+    unsigned long long d = ag.dropped;                                 // one atomic per warp, and only if something was dropped
+    for (int o = 16; o; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+    if ((threadIdx.x & 31u) == 0 && d) atomicAdd(&T.m_dropped[0], d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -501,7 +509,7 @@ __host__ __device__ inline SmemLayout smem_layout(const DevTables &T, uint32_t t
 __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, const SmemLayout &L, uint32_t n_bars, Tabs &tb, MetricAgg &ag)
 {
     ag.keys = (unsigned long long *)(smem + L.agg_keys);
-    ag.counts = (unsigned int *)(smem + L.agg_counts);
+    ag.counts = (unsigned int *)(smem + L.agg_counts); ag.dropped = 0ull;
     for (uint32_t i = threadIdx.x; i < MSLOTS; i += blockDim.x) { ag.keys[i] = 0ull; ag.counts[i] = 0u; }
     uint64_t *bars = (uint64_t *)(smem + L.bars);
     tb.ep = T.ep_slots; tb.ep_mask = T.ep_mask; tb.ep_shift = T.ep_shift; tb.rowq = T.ep_rowq;
@@ -824,7 +832,7 @@ __global__ void k_counters_export(const __grid_constant__ DevTables T, clk_metri
 __global__ void k_counters_clear(const __grid_constant__ DevTables T)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.m_mask; i += gridDim.x * blockDim.x) { T.m_keys[i] = 0ull; T.m_counts[i] = 0ull; }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *T.m_dropped = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { T.m_dropped[0] = 0ull; T.m_dropped[1] = 0ull; }
 }
 __global__ void k_counters_import(const __grid_constant__ DevTables T, const clk_metric *__restrict__ blocks, unsigned long long rows)
 {
@@ -833,8 +841,8 @@ __global__ void k_counters_import(const __grid_constant__ DevTables T, const clk
         if (m.count == 0) continue;
         uint32_t h = mix64(m.key.cgroup_id) & T.cg_mask, crow = 0xffffffffu;
         if (T.n_crows) for (;;) { uint32_t s = T.cg_slots[h]; if (!s) break; if (T.crows[s - 1].cgroup_id == m.key.cgroup_id) { crow = s - 1; break; } h = (h + 1) & T.cg_mask; }
-        if (crow == 0xffffffffu) { atomicAdd(T.m_dropped, m.count); continue; }
-        metric_global_add(T, metric_pack(m.key.domain_hash, m.key.dst_port, crow, m.key.action), m.count);
+        if (crow == 0xffffffffu) { atomicAdd(&T.m_dropped[0], m.count); continue; }
+        { unsigned long long dr = metric_global_add(T, metric_pack(m.key.domain_hash, m.key.dst_port, crow, m.key.action), m.count); if (dr) atomicAdd(&T.m_dropped[0], dr); }
     }
 }
 

@@ -129,7 +129,8 @@ struct DevTables {
     uint32_t coredns_ips[8];     uint32_t n_coredns;     // distinct cfg.coredns_ip values (DNS-answer stage)
     // device metrics table
     unsigned long long *m_keys;  unsigned long long *m_counts; uint32_t m_mask;
-    unsigned long long *m_dropped;
+    unsigned long long *m_dropped;                       // [0] increments dropped, [1] keys present
+    uint32_t m_max;                                      // max_entries of metrics_map (common.h:173): inserts beyond it are dropped
     // sizes for optional shared-memory staging (bytes; 0 = do not stage)
     uint32_t stage_ep_bytes, stage_soa_bytes, stage_dns_bytes, stage_route_bytes, stage_pre_bytes;
 };

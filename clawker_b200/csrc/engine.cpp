@@ -358,7 +358,7 @@ int publish_locked(clk_engine *e)
     }
     std::sort(T.coredns_ips, T.coredns_ips + T.n_coredns);
     T.m_keys = (unsigned long long *)e->m_keys.p; T.m_counts = (unsigned long long *)e->m_counts.p;
-    T.m_mask = e->T.m_mask; T.m_dropped = (unsigned long long *)e->m_dropped.p;
+    T.m_mask = e->T.m_mask; T.m_dropped = (unsigned long long *)e->m_dropped.p; T.m_max = e->max_metrics;
     // shared-memory staging budget: endpoints <= 256 rows, dns <= 32 KiB, route <= 8 KiB
     if (e->stage_tables) {
         if (n_ep4 && rows.size() <= 256) { T.stage_ep_bytes = (uint32_t)ep_slots.size() * 8; T.stage_soa_bytes = (uint32_t)rowq.size() * 16; }
@@ -431,10 +431,10 @@ int clk_engine_create(const clk_cfg *cfg, clk_engine **out)
         for (int i = 0; i < 3; i++) cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking);
         e->stats.sm_count = (uint32_t)n_sm;
         uint32_t slots = pow2_at_least((uint64_t)e->max_metrics * 2);
-        if (e->m_keys.ensure((size_t)slots * 8) != cudaSuccess || e->m_counts.ensure((size_t)slots * 8) != cudaSuccess || e->m_dropped.ensure(8) != cudaSuccess) {
+        if (e->m_keys.ensure((size_t)slots * 8) != cudaSuccess || e->m_counts.ensure((size_t)slots * 8) != cudaSuccess || e->m_dropped.ensure(16) != cudaSuccess) {
             int r = fail(nullptr, CLK_ENOMEM, "cudaMalloc metrics table (%u slots)", slots); delete e; return r;
         }
-        cudaMemset(e->m_keys.p, 0, (size_t)slots * 8); cudaMemset(e->m_counts.p, 0, (size_t)slots * 8); cudaMemset(e->m_dropped.p, 0, 8);
+        cudaMemset(e->m_keys.p, 0, (size_t)slots * 8); cudaMemset(e->m_counts.p, 0, (size_t)slots * 8); cudaMemset(e->m_dropped.p, 0, 16);
         e->T.m_mask = slots - 1;
     }
     *out = e;
@@ -821,7 +821,7 @@ int clk_counters_export(clk_engine *e, void *d_block, void *stream)
 static DevTables global_view(clk_engine *e)
 {
     DevTables G = e->T;
-    G.m_keys = (unsigned long long *)e->g_keys.p; G.m_counts = (unsigned long long *)e->g_counts.p; G.m_dropped = (unsigned long long *)e->g_dropped.p;
+    G.m_keys = (unsigned long long *)e->g_keys.p; G.m_counts = (unsigned long long *)e->g_counts.p; G.m_dropped = (unsigned long long *)e->g_dropped.p; G.m_max = 0xffffffffu;
     return G;
 }
 
@@ -833,7 +833,7 @@ int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, 
     int rc = ensure_published(e); if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     const size_t slots = (size_t)e->T.m_mask + 1;
-    CUDA_TRY(e, e->g_keys.ensure(slots * 8)); CUDA_TRY(e, e->g_counts.ensure(slots * 8)); CUDA_TRY(e, e->g_dropped.ensure(8));
+    CUDA_TRY(e, e->g_keys.ensure(slots * 8)); CUDA_TRY(e, e->g_counts.ensure(slots * 8)); CUDA_TRY(e, e->g_dropped.ensure(16));
     DevTables G = global_view(e);
     const char *err = launch_counters_clear(G, st);
     if (!err) err = launch_counters_import(G, (const clk_metric *)d_blocks, (unsigned long long)n_blocks * slots, st);
