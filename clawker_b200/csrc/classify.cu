@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "dev_tables.h"
 #include "classify.h"
 
@@ -544,9 +545,16 @@ __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, 
 
 // The common case as one predicated ladder.  Inputs: bytes 12..15 (w3), 16..31 (q1), 32..39 (q2x, q2y).
 // Returns false when the packet is not "simple IPv4" and must take the generic path.
+// nm (name-stage work this packet still needs): 0 none, NM_DNSQ / NM_DNSQ_TCP / NM_TLS / NM_DNSA.
+#define NM_NONE 0u
+#define NM_DNSQ 1u
+#define NM_DNSQ_TCP 2u
+#define NM_TLS 3u
+#define NM_DNSA 4u
 __device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb, uint32_t w3, const uint4 &q1, uint32_t q2x, uint32_t q2y,
-                                              uint32_t &word, bool &hm, unsigned long long &mk)
+                                              uint32_t q2w, uint32_t avail, uint32_t flags, uint32_t &word, bool &hm, unsigned long long &mk, uint32_t &nm)
 {
+    nm = NM_NONE;
     // Ethernet II + IPv4 without options, not a later fragment
     if ((w3 & 0x00ffffffu) != 0x00450008u || (q1.y & 0xff1fu) != 0) return false;
     const uint32_t proto = q1.y >> 24;
@@ -558,7 +566,10 @@ __device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb
     bool ingress = false;
     if (r < 0 && udp) { r = ep_find(tb, dst); ingress = r >= 0; }
     word = 0; hm = false; mk = 0;
-    if (r < 0) return true;                                                      // no endpoint: no socket event
+    if (r < 0) {                                                                 // no endpoint: no socket event ...
+        if ((flags & CLK_F_NAME_STAGE) && udp && sport == 53 && is_coredns(T, dst)) nm = NM_DNSA;   // ... but maybe an upstream answer reaching CoreDNS
+        return true;
+    }
 
     const uint4 *rq = tb.rowq + 3 * r;
     const uint4 ra = rq[0], rb = rq[1], rc = rq[2];
@@ -603,6 +614,15 @@ __device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb
         w |= (nport & 0xffffu) << 8;
     }
     word = w;
+    if ((flags & CLK_F_NAME_STAGE) && enf && !ingress && !raw && verdict != CLK_V_DENY) {
+        const uint32_t fip = verdict == CLK_V_REWRITE ? nip : ip, fport = verdict == CLK_V_REWRITE ? nport : port;
+        // TCP payload length from the header words already in registers (q2w = bytes 44..47: data offset is byte 46)
+        uint32_t end = 14 + bswap16(q1.x); if (end > avail) end = avail;
+        const uint32_t doff = ((q2w >> 20) & 0xfu) * 4, po = 34 + doff;
+        const bool tcp_payload = tcp && doff >= 20 && po < end;
+        if (fip == coredns && fport == 53) { if (udp) nm = NM_DNSQ; else if (tcp_payload) nm = NM_DNSQ_TCP; }
+        else if (tcp_payload && fip == envoy && fport == egress_port) nm = NM_TLS;
+    }
     if (metric) { hm = true; mk = ((unsigned long long)((mp & 0xffffu) | (crow << 16) | (metric << 30)) << 32) | mh; }   // == metric_pack
     return true;
 }
@@ -655,7 +675,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
         const uint32_t i = (t << 5) + lane;
         bool hm = false, slow = false; unsigned long long mk = 0; uint32_t w = 0;
         if (i < n) {
-            slow = !fast_classify(T, tb, w3, q1, q2.x, q2.y, w, hm, mk);
+            uint32_t nm; slow = !fast_classify(T, tb, w3, q1, q2.x, q2.y, 0, 64, gflags, w, hm, mk, nm);
             if (!slow) stg_stream(&verdicts[i], w);
         }
         const unsigned sm = __ballot_sync(0xffffffffu, slow);
@@ -685,6 +705,114 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
         }
         if (do_metrics) metric_warp_emit(T, ag, hm2, mk2);
     }
+    if (do_metrics) metric_cta_flush(T, ag);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1b: variable-length captures with the name stage (BASELINE config 3)
+// ------------------------------------------------------------------------------------------------
+// Phase A (every packet, all lanes converged): the same predicated L3/L4 ladder as the slot kernel on the
+// first 40 header bytes, which also says what payload work is left (nm).  Packets that need payload work
+// are NOT parsed in place — byte-serial parsing with one lane active would dominate the kernel — they are
+// compacted into per-warp queues BY TYPE, and each queue is drained 32 packets at a time, so that all 32
+// lanes run the same parser (DNS question, TLS ClientHello, DNS answer, or the generic path for rare frames).
+#define VL_WARPS 16
+#define VL_QUEUES 5            // generic, dns query (udp), dns query (tcp), tls, dns answer
+#define VL_QCAP 64
+
+__device__ __forceinline__ void payload_window(const uint8_t *pk, uint32_t avail, bool tcp, uint32_t &po, uint32_t &pl)
+{
+    // simple IPv4 (ihl 5): l4off = 34; same arithmetic as name_stage()
+    uint32_t end = 14 + gbe16(pk + 16); if (end > avail) end = avail;
+    po = 0; pl = 0;
+    if (!tcp) { po = 42; if (po <= end) pl = end - po; }
+    else if (34 + 13 <= avail) { uint32_t doff = (gb(pk + 46) >> 4) * 4; po = 34 + doff; if (doff >= 20 && po <= end) pl = end - po; }
+}
+
+__device__ __noinline__ uint32_t name_work(const DevTables &T, const uint8_t *pk, uint32_t avail, uint32_t type, uint32_t word)
+{
+    uint32_t po, pl;
+    if (type == NM_DNSA) {
+        uint32_t end = 14 + gbe16(pk + 16); if (end > avail) end = avail;
+        if (42 > end) return 0;
+        uint32_t nv, nupd = dns_answer_updates(T, pk + 42, end - 42, 0, nullptr, 0, 0, &nv);
+        return (nv << 4) | (nupd << 27);
+    }
+    payload_window(pk, avail, type != NM_DNSQ, po, pl);
+    uint32_t name = CLK_N_NA;
+    if (type == NM_DNSQ) name = dns_query_verdict(T, pk + po, pl);
+    else if (type == NM_DNSQ_TCP) { if (pl > 0) name = (pl >= 2 && gbe16(pk + po) + 2 <= pl) ? dns_query_verdict(T, pk + po + 2, gbe16(pk + po)) : CLK_N_DENY; }
+    else if (pl > 0) name = tls_sni_verdict(T, pk + po, pl);
+    return word | (name << 4);
+}
+
+__global__ void __launch_bounds__(VL_WARPS * 32, 2) k_varlen_fast(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts,
+                                                                  const uint32_t *__restrict__ offs16, unsigned long long n,
+                                                                  uint32_t flags, uint32_t *__restrict__ verdicts)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const SmemLayout L = smem_layout(T, 0, VL_WARPS * VL_QUEUES * VL_QCAP * 8, 0);
+    Tabs tb; MetricAgg ag;
+    cta_prologue(T, smem, L, 0, tb, ag);
+    __syncthreads();
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint2 *queue = (uint2 *)(smem + L.queue) + warp * (VL_QUEUES * VL_QCAP);      // entry: {packet index, phase-A word}
+    const uint32_t n32 = (uint32_t)n, n_tiles = (n32 + 31u) >> 5;
+    const uint32_t gw = blockIdx.x * VL_WARPS + warp, W = gridDim.x * VL_WARPS;
+    const bool do_metrics = !(flags & CLK_F_NO_METRICS);
+    uint32_t qn[VL_QUEUES];
+    #pragma unroll
+    for (int k = 0; k < VL_QUEUES; k++) qn[k] = 0;
+
+    // drain up to 32 entries of queue k, every participating lane running the same parser
+    auto drain = [&](int k, uint32_t take) {
+        uint2 ent = make_uint2(0, 0);
+        if (lane < take) ent = queue[k * VL_QCAP + lane];
+        const uint2 carry = (lane + 32 < qn[k]) ? queue[k * VL_QCAP + lane + 32] : make_uint2(0, 0);
+        bool hm = false; unsigned long long mk = 0;
+        if (lane < take) {
+            const uint32_t o0 = __ldg(&offs16[ent.x]), o1 = __ldg(&offs16[ent.x + 1]);
+            const uint8_t *pk = pkts + (unsigned long long)o0 * 16ull; const uint32_t avail = (o1 - o0) * 16u;
+            uint32_t w = k == 0 ? generic_one(T, tb, pk, avail, flags, hm, mk) : name_work(T, pk, avail, (uint32_t)k, ent.y);
+            stg_stream(&verdicts[ent.x], w);
+        }
+        if (k == 0 && do_metrics) metric_warp_emit(T, ag, hm, mk);
+        __syncwarp();
+        if (lane + 32 < qn[k]) queue[k * VL_QCAP + lane] = carry;
+        qn[k] -= take;
+        __syncwarp();
+    };
+
+    for (uint32_t t = gw; t < n_tiles; t += W) {
+        const uint32_t i = (t << 5) + lane;
+        bool hm = false; unsigned long long mk = 0; uint32_t w = 0, kind = 0xffu;   // kind: queue to join, 0xff = done in phase A
+        if (i < n32) {
+            const uint32_t o0 = __ldg(&offs16[i]), o1 = __ldg(&offs16[i + 1]);
+            const uint8_t *pk = pkts + (unsigned long long)o0 * 16ull; const uint32_t avail = (o1 - o0) * 16u;
+            kind = 0;
+            if (avail >= 64) {
+                const uint32_t w3 = __ldg((const uint32_t *)(pk + 12));
+                const uint4 q1 = __ldg((const uint4 *)(pk + 16));
+                const uint4 q2 = __ldg((const uint4 *)(pk + 32));
+                uint32_t nm;
+                if (fast_classify(T, tb, w3, q1, q2.x, q2.y, q2.w, avail, flags, w, hm, mk, nm)) kind = nm == NM_NONE ? 0xffu : nm;
+            }
+            if (kind == 0xffu) stg_stream(&verdicts[i], w);
+        }
+        if (do_metrics) metric_warp_emit(T, ag, hm, mk);
+        #pragma unroll
+        for (int k = 0; k < VL_QUEUES; k++) {
+            const unsigned m = __ballot_sync(0xffffffffu, kind == (uint32_t)k);
+            if (m) {
+                if (kind == (uint32_t)k) queue[k * VL_QCAP + qn[k] + __popc(m & ((1u << lane) - 1u))] = make_uint2(i, w);
+                qn[k] += __popc(m);
+                __syncwarp();
+                if (qn[k] >= 32) drain(k, 32);
+            }
+        }
+    }
+    #pragma unroll
+    for (int k = 0; k < VL_QUEUES; k++) if (qn[k]) drain(k, qn[k]);
     if (do_metrics) metric_cta_flush(T, ag);
 }
 
@@ -939,6 +1067,15 @@ const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t
 {
     if (n == 0) return nullptr;
     int grid = 0; cudaError_t e;
+    if (n < 0x7fffffffull && !getenv("CLK_VARLEN_GENERIC")) {
+        SmemLayout L = smem_layout(T, 0, VL_WARPS * VL_QUEUES * VL_QCAP * 8, 0);
+        if ((e = occupancy_grid(k_varlen_fast, VL_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
+        unsigned long long need = ((n + 31) / 32 + VL_WARPS - 1) / VL_WARPS; if ((unsigned long long)grid > need) grid = (int)need;
+        k_varlen_fast<<<grid, VL_WARPS * 32, L.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, n, flags, d_verdicts);
+        if (info) { info->grid = grid; info->block = VL_WARPS * 32; info->smem = L.total; }
+        e = cudaGetLastError();
+        return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+    }
     SmemLayout L = smem_layout(T, 0, 0, 0);
     if ((e = occupancy_grid(k_generic<true>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long need = (n + 255) / 256; if ((unsigned long long)grid > need) grid = (int)need;

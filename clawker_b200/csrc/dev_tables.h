@@ -32,15 +32,17 @@ CLK_HD uint32_t mix64(uint64_t x)
     return (uint32_t)x;
 }
 
-// Polynomial name hash over lower-cased bytes, mod 2^64: H(s) = sum s[i] * B^(n-1-i).
-// Suffix hashes come out of one forward pass: H(s[k:]) = H(s) - H(s[:k]) * B^(n-k).
-// A hit is always confirmed by a byte compare against the stored name, so the hash only
-// has to be a good filter (collisions cost time, never correctness).
-static const uint64_t NAME_B    = 0x9E3779B97F4A7C15ull;          // odd
-static const uint64_t NAME_BINV = 0xF1DE83E19937733Dull;          // NAME_B * NAME_BINV == 1 (mod 2^64)
-CLK_HD uint64_t name_key(uint64_t suffix_hash, uint32_t len)
+// Name hash: two independent 32-bit polynomial hashes over the lower-cased bytes, low power first:
+//   h(s) = sum s[j] * B^j  (mod 2^32),  B in {NAME_B1, NAME_B2}.
+// A right-to-left Horner pass yields h of every suffix as it goes; a left-to-right pass yields them through
+// h(s[k:]) = (F - P_k) * B^-k with F the whole-string sum and P_k the prefix sum (B is odd, so invertible).
+// A hit is always confirmed byte-for-byte against the stored name, so the hash only has to be a good filter
+// (collisions cost time, never correctness).
+static const uint32_t NAME_B1 = 0x9E3779B1u, NAME_B1INV = 0x0E8B2F51u;      // B1 * B1INV == 1 (mod 2^32)
+static const uint32_t NAME_B2 = 0x85EBCA77u, NAME_B2INV = 0xB6C92F47u;
+CLK_HD uint64_t name_key(uint32_t h1, uint32_t h2, uint32_t len)
 {
-    uint64_t k = suffix_hash ^ ((uint64_t)len * 0xD6E8FEB86659FD93ull);
+    uint64_t k = (((uint64_t)h2 << 32) | h1) ^ ((uint64_t)len * 0xD6E8FEB86659FD93ull);
     return k ? k : 1;                                              // 0 is the empty-slot marker
 }
 

@@ -126,11 +126,11 @@ bool is_cidr_mask(uint32_t mask_nbo)
 }
 int mask_plen(uint32_t mask_nbo) { return __builtin_popcount(mask_nbo); }
 
-uint64_t poly_hash(const std::string &s)
+uint64_t name_key_of(const std::string &s)
 {
-    uint64_t h = 0;
-    for (unsigned char c : s) { if (c >= 'A' && c <= 'Z') c = (unsigned char)(c + 32); h = h * NAME_B + c; }
-    return h;
+    uint32_t h1 = 0, h2 = 0, p1 = 1, p2 = 1;
+    for (unsigned char c : s) { if (c >= 'A' && c <= 'Z') c = (unsigned char)(c + 32); h1 += c * p1; h2 += c * p2; p1 *= NAME_B1; p2 *= NAME_B2; }
+    return name_key(h1, h2, (uint32_t)s.size());
 }
 
 // Build one name table (slots + blob entries appended to `blob`).
@@ -145,7 +145,7 @@ void build_name_table(const std::vector<std::string> &names, const std::vector<u
         uint32_t off = (uint32_t)blob.size();
         blob.push_back((uint8_t)s.size());
         for (unsigned char c : s) blob.push_back((c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c);
-        uint64_t key = name_key(poly_hash(s), (uint32_t)s.size());
+        uint64_t key = name_key_of(s);
         uint32_t h = mix64(key) & (cap - 1);
         while (slots[h].key) h = (h + 1) & (cap - 1);
         slots[h] = NameSlot{ key, vals[i], off };

@@ -70,44 +70,126 @@ __device__ __forceinline__ bool dns_name_equals(const uint8_t *m, uint32_t mlen,
 // CoreDNS zone selection on the name at m[off..]: longest label suffix that is a configured zone.
 // Returns 1 (+ zone DomainHash) for a non-root zone, 0 for ".", -1 if the name is malformed.
 // *after = offset just past the name as stored.
+//
+// Exact, simple form (re-hashes every candidate suffix): only reached when a hash hit fails its byte
+// confirmation in the converged routine below, i.e. on a 64-bit hash collision.
+__device__ __noinline__ int dns_zone_select_exact(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t off, uint32_t *after, uint32_t *zone_hash)
+{
+    NameWalk w; w.init(m, mlen, off);
+    int labels = 0, last_bad = -1, c;
+    while ((c = w.next_label()) > 0) {
+        for (int i = 0; i < c; i++) if (!zone_char(lower(gb(m + w.p + i)))) last_bad = labels;
+        labels++; w.p += c;
+    }
+    if (c < 0) return -1;
+    *after = w.after;
+    if (T.zone_slots == nullptr) return 0;
+    w.init(m, mlen, off);
+    for (int lab = 0; (c = w.next_label()) > 0; lab++) {
+        const uint32_t lab_off = w.p - 1;
+        if (lab > last_bad) {
+            NameWalk v; v.init(m, mlen, lab_off);                   // hash the suffix starting at this label
+            uint32_t h1 = 0, h2 = 0, p1 = 1, p2 = 1, len = 0; int cc; bool first = true;
+            while ((cc = v.next_label()) > 0) {
+                if (!first) { h1 += '.' * p1; h2 += '.' * p2; p1 *= NAME_B1; p2 *= NAME_B2; len++; }
+                first = false;
+                for (int i = 0; i < cc; i++) { uint32_t ch = lower(gb(m + v.p + i)); h1 += ch * p1; h2 += ch * p2; p1 *= NAME_B1; p2 *= NAME_B2; len++; }
+                v.p += cc;
+            }
+            const uint64_t key = name_key(h1, h2, len);
+            uint32_t h = mix64(key) & T.zone_mask; NameSlot s;
+            while (name_table_find(T.zone_slots, T.zone_mask, key, h, s)) {
+                const uint8_t *str = T.names + s.str_off;
+                if (str[0] == len && dns_name_equals(m, mlen, lab_off, str + 1, len)) { *zone_hash = s.val; return 1; }
+            }
+        }
+        w.p += c;
+    }
+    return 0;
+}
+
+// Converged form: a warp whose 32 lanes each hold a different DNS name advances label by label in lock step
+// through two forward passes (F = whole-name sum, then prefix sums), every lane stops at its FIRST hash
+// hit (the longest matching suffix), and the byte-for-byte confirmation runs once after the loop.
 __device__ __forceinline__ int dns_zone_select(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t off, uint32_t *after, uint32_t *zone_hash)
 {
-    // pass 1: total hash H, text length n, B^n, last label holding a byte no zone can contain
+    // Common case first: an uncompressed name shorter than 64 octets (every real question name).  Hop over the
+    // length octets once (remembering where they are in a 64-bit mask), then ONE right-to-left Horner pass
+    // yields the hash of every label suffix; lanes move label by label in lock step; the longest hash hit is
+    // confirmed once at the end.  Anything else (pointers, long names, malformed) takes the general path below.
+    {
+        uint32_t pos = off; unsigned long long lm = 0ull; bool simple = true;
+        for (;;) {
+            if (pos >= mlen) { simple = false; break; }
+            const uint32_t l = gb(m + pos);
+            if (l == 0) break;
+            if ((l & 0xC0u) || pos + 1 + l > mlen || pos + 1 + l - off >= 64) { simple = false; break; }
+            lm |= 1ull << (pos - off);
+            pos += 1 + l;
+        }
+        if (simple) {
+            const uint32_t end = pos;                           // the root label's zero octet
+            *after = end + 1;
+            if (end == off || T.zone_slots == nullptr) return 0;
+            uint32_t S1 = 0, S2 = 0, i = end, hit_off = 0, hit_len = 0; bool bad = false, found = false; NameSlot hit, cand;
+            for (;;) {
+                bool isl;
+                do {
+                    i--;
+                    const uint32_t b = gb(m + i);
+                    isl = (lm >> (i - off)) & 1ull;
+                    if (!isl) { const uint32_t ch = lower(b); bad |= !zone_char(ch); S1 = ch + NAME_B1 * S1; S2 = ch + NAME_B2 * S2; }
+                } while (!isl);
+                if (bad) break;                                 // no zone can contain this label, nor any longer suffix
+                const uint64_t key = name_key(S1, S2, end - i - 1);
+                uint32_t h = mix64(key) & T.zone_mask;
+                if (name_table_find(T.zone_slots, T.zone_mask, key, h, cand)) { found = true; hit = cand; hit_off = i; hit_len = end - i - 1; }
+                if (i == off) break;
+                S1 = '.' + NAME_B1 * S1; S2 = '.' + NAME_B2 * S2;
+            }
+            if (!found) return 0;
+            const uint8_t *str = T.names + hit.str_off;
+            if (str[0] == hit_len && dns_name_equals(m, mlen, hit_off, str + 1, hit_len)) { *zone_hash = hit.val; return 1; }
+            return dns_zone_select_exact(T, m, mlen, off, after, zone_hash);
+        }
+    }
     NameWalk w; w.init(m, mlen, off);
-    uint64_t H = 0, Bn = 1; uint32_t n = 0; int labels = 0, last_bad = -1, c;
+    uint32_t F1 = 0, F2 = 0, p1 = 1, p2 = 1, n = 0; int labels = 0, last_bad = -1, c;
     while ((c = w.next_label()) > 0) {
-        if (labels) { H = H * NAME_B + '.'; Bn *= NAME_B; n++; }
+        if (labels) { F1 += '.' * p1; F2 += '.' * p2; p1 *= NAME_B1; p2 *= NAME_B2; n++; }
         for (int i = 0; i < c; i++) {
-            uint32_t b = lower(gb(m + w.p + i));
+            const uint32_t b = lower(gb(m + w.p + i));
             if (!zone_char(b)) last_bad = labels;
-            H = H * NAME_B + b; Bn *= NAME_B; n++;
+            F1 += b * p1; F2 += b * p2; p1 *= NAME_B1; p2 *= NAME_B2; n++;
         }
         labels++; w.p += c;
     }
     if (c < 0) return -1;
     *after = w.after;
     if (T.zone_slots == nullptr) return 0;
-    // pass 2: prefix hash P and R = B^(n-k); suffix at label start k: H - P*R
     w.init(m, mlen, off);
-    uint64_t P = 0, R = Bn; uint32_t k = 0; int lab = 0;
+    uint32_t P1 = 0, P2 = 0, i1 = 1, i2 = 1, k = 0, hit_off = 0, hit_len = 0; p1 = 1; p2 = 1;
+    int lab = 0; bool found = false; NameSlot hit;
     for (;;) {
-        uint32_t lab_off = w.p;                    // may be a pointer; next_label resolves it, so re-read below
         c = w.next_label();
         if (c <= 0) break;
-        lab_off = w.p - 1;
-        if (lab) { P = P * NAME_B + '.'; R *= NAME_BINV; k++; }
+        const uint32_t lab_off = w.p - 1;
+        if (lab) { P1 += '.' * p1; P2 += '.' * p2; p1 *= NAME_B1; p2 *= NAME_B2; i1 *= NAME_B1INV; i2 *= NAME_B2INV; k++; }
         if (lab > last_bad) {
-            uint64_t key = name_key(H - P * R, n - k);
-            uint32_t h = mix64(key) & T.zone_mask; NameSlot s;
-            while (name_table_find(T.zone_slots, T.zone_mask, key, h, s)) {
-                const uint8_t *str = T.names + s.str_off;
-                if (str[0] == n - k && dns_name_equals(m, mlen, lab_off, str + 1, n - k)) { *zone_hash = s.val; return 1; }
-            }
+            const uint64_t key = name_key((F1 - P1) * i1, (F2 - P2) * i2, n - k);
+            uint32_t h = mix64(key) & T.zone_mask;
+            if (name_table_find(T.zone_slots, T.zone_mask, key, h, hit)) { found = true; hit_off = lab_off; hit_len = n - k; break; }
         }
-        for (int i = 0; i < c; i++) { P = P * NAME_B + lower(gb(m + w.p + i)); R *= NAME_BINV; k++; }
+        for (int i = 0; i < c; i++) {
+            const uint32_t b = lower(gb(m + w.p + i));
+            P1 += b * p1; P2 += b * p2; p1 *= NAME_B1; p2 *= NAME_B2; i1 *= NAME_B1INV; i2 *= NAME_B2INV; k++;
+        }
         lab++; w.p += c;
     }
-    return 0;
+    if (!found) return 0;
+    const uint8_t *str = T.names + hit.str_off;
+    if (str[0] == hit_len && dns_name_equals(m, mlen, hit_off, str + 1, hit_len)) { *zone_hash = hit.val; return 1; }
+    return dns_zone_select_exact(T, m, mlen, off, after, zone_hash);
 }
 
 // DNS query arriving at CoreDNS (miekg/dns defaultMsgAcceptFunc, then ServeDNS zone routing).
@@ -213,24 +295,41 @@ __device__ __forceinline__ bool sni_equals(const uint8_t *host, uint32_t from, u
     return true;
 }
 
+__device__ __noinline__ bool sni_match_exact(const DevTables &T, const uint8_t *host, uint32_t n)
+{
+    // simple form: re-hash every candidate suffix (whole name, then each '.' at 1 <= pos < n - 1)
+    if (T.sni_slots == nullptr) return false;
+    for (uint32_t pos = 0; pos < n; pos++) {
+        if (!(pos == 0 || (lower(gb(host + pos)) == '.' && pos + 1 < n))) continue;
+        uint32_t h1 = 0, h2 = 0, p1 = 1, p2 = 1;
+        for (uint32_t i = pos; i < n; i++) { uint32_t ch = lower(gb(host + i)); h1 += ch * p1; h2 += ch * p2; p1 *= NAME_B1; p2 *= NAME_B2; }
+        const uint64_t key = name_key(h1, h2, n - pos);
+        uint32_t h = mix64(key) & T.sni_mask; NameSlot s;
+        while (name_table_find(T.sni_slots, T.sni_mask, key, h, s))
+            if (sni_equals(host, pos, n, T.names + s.str_off)) return true;
+    }
+    return false;
+}
+
+// Converged form: one right-to-left Horner pass gives the hash of every suffix; lanes move from candidate
+// to candidate in lock step (any match allows, so the order is irrelevant), stop at their first hash hit and
+// confirm once after the loop.
 __device__ __forceinline__ bool sni_match(const DevTables &T, const uint8_t *host, uint32_t n)
 {
     if (T.sni_slots == nullptr) return false;
-    uint64_t H = 0, Bn = 1;
-    for (uint32_t i = 0; i < n; i++) { H = H * NAME_B + lower(gb(host + i)); Bn *= NAME_B; }
-    uint64_t P = 0, R = Bn;
-    for (uint32_t pos = 0; pos < n; pos++) {
-        uint32_t c = lower(gb(host + pos));
-        // candidates: the whole name (pos 0), then every '.' at index >= 1 with pos < n - 1
-        if (pos == 0 || (c == '.' && pos + 1 < n)) {
-            uint64_t key = name_key(H - P * R, n - pos);
-            uint32_t h = mix64(key) & T.sni_mask; NameSlot s;
-            while (name_table_find(T.sni_slots, T.sni_mask, key, h, s))
-                if (sni_equals(host, pos, n, T.names + s.str_off)) return true;
-        }
-        P = P * NAME_B + c; R *= NAME_BINV;
+    uint32_t S1 = 0, S2 = 0, i = n; bool found = false; NameSlot hit;
+    for (;;) {
+        uint32_t c;
+        do { i--; c = lower(gb(host + i)); S1 = c + NAME_B1 * S1; S2 = c + NAME_B2 * S2; } while (i > 0 && !(c == '.' && i + 1 < n));
+        // here: i == 0 (the whole name) or host[i] is a '.' with 1 <= i < n - 1 (Envoy's wildcard candidates)
+        const uint64_t key = name_key(S1, S2, n - i);
+        uint32_t h = mix64(key) & T.sni_mask;
+        if (name_table_find(T.sni_slots, T.sni_mask, key, h, hit)) { found = true; break; }
+        if (i == 0) break;
     }
-    return false;
+    if (!found) return false;
+    if (sni_equals(host, i, n, T.names + hit.str_off)) return true;
+    return sni_match_exact(T, host, n);
 }
 
 __device__ __forceinline__ uint32_t tls_sni_verdict(const DevTables &T, const uint8_t *p, uint32_t n)
