@@ -33,10 +33,13 @@ import numpy as np
 
 METRIC = "Mpackets/sec egress-verdict throughput"
 WORKLOADS = {
-    "c2": dict(n=10_000_000, gen=2_000_000, desc="10M-packet synthetic pcap (64 B slots), 1k IP/CIDR rules, 8 containers"),
-    "c5": dict(n=100_000_000, gen=2_000_000, desc="64 B min-size packet flood, 100M packets/GPU"),
+    "c2": dict(n=10_000_000, gen=2_000_000, layout="slots", cfg="c2",
+               desc="10M-packet synthetic pcap (64 B slots), 1k IP/CIDR rules, 8 containers"),
+    "c3": dict(n=100_000_000, gen=1_000_000, layout="varlen", cfg="c3",
+               desc="100M packets incl. DNS + TLS-SNI (70/10/5/15 % header-only/DNS query/DNS answer/ClientHello), 10k-domain allowlist, name stage on"),
+    "c5": dict(n=100_000_000, gen=2_000_000, layout="slots", cfg="c5:1000", desc="64 B min-size packet flood, 100M packets/GPU"),
 }
-BYTES_PER_PACKET = 68          # 64 B slot read + 4 B verdict write
+# Algorithmic bytes per packet: captured bytes + 4 B verdict (+ 4 B offset in varlen mode).
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -83,15 +86,33 @@ def make_batch(workload: str, rank: int):
     """Synthetic capture of the named shape; `gen` unique packets tiled to n (HBM does not care)."""
     from clawker_b200 import capture
     spec = WORKLOADS[workload]
-    w = capture.make_workload("c2" if workload == "c2" else "c5:1000")
-    pk = capture.gen_slots(w, spec["gen"], seed=2 + 1000 * rank)
-    return w, pk, spec
+    w = capture.make_workload(spec["cfg"])
+    if spec["layout"] == "slots":
+        return w, (capture.gen_slots(w, spec["gen"], seed=2 + 1000 * rank), None), spec
+    blob, offs, _ = capture.gen_varlen(w, spec["gen"], seed=3 + 1000 * rank, pool=8192)
+    return w, (blob, offs), spec
+
+
+def tile_host(batch, reps: int):
+    """Repeat a host batch `reps` times (CPU baseline / e2e samples)."""
+    pk, offs = batch
+    if offs is None:
+        return np.tile(pk, (reps, 1)), None
+    per = int(offs[-1])
+    o = np.concatenate([offs[:-1].astype(np.int64) + k * per for k in range(reps)] + [np.array([reps * per], dtype=np.int64)])
+    return np.tile(pk, reps), o.astype(np.uint32)
+
+
+def batch_packets(batch) -> int:
+    return batch[0].shape[0] if batch[1] is None else batch[1].size - 1
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_baseline(w, pk: np.ndarray, steps: int = 1) -> dict:
+def cpu_baseline(w, batch, steps: int = 1, name_stage: bool = False) -> dict:
     """The reference's own decision code on this box's host cores (kind "reference" = /root/reference's
-    clawker.c compiled for the host in oracle/_ref; "port" = the C restatement).  Bounded sample."""
+    clawker.c compiled for the host in oracle/_ref; "port" = the C restatement).  Bounded sample.  With the
+    name stage on, the CoreDNS / Envoy / dnsbpf stages around it are the oracle's restatement in both kinds
+    (third-party code, not in the reference tree)."""
     from oracle import oracle, rules_oracle
     kind = "reference" if oracle.have_ref() else "port"
     o = oracle.Oracle("ref" if kind == "reference" else "port")
@@ -100,17 +121,18 @@ def cpu_baseline(w, pk: np.ndarray, steps: int = 1) -> dict:
     t.update(zones=c.zones, snis=c.snis, routes=dict(c.routes), cidrs=[] if kind == "reference" else list(c.cidrs))
     o.load(t)
     cores = os.cpu_count() or 1
-    reps = max(1, (250_000 * cores) // pk.shape[0])                 # ~0.25 M packets per thread: 10-30 CPU-seconds per step
-    if reps > 1:
-        pk = np.tile(pk, (reps, 1))
-    o.classify(pk[: 200_000], nthreads=cores)                       # warm the tables
+    npk = batch_packets(batch)
+    reps = max(1, (250_000 * cores) // npk)                         # ~0.25 M packets per thread: 10-30 CPU-seconds per step
+    pk, offs = tile_host(batch, reps) if reps > 1 else batch
+    flags = 1 if name_stage else 0
+    n_s = batch_packets((pk, offs))
     best = 0.0
-    for _ in range(max(1, steps)):
+    for _ in range(max(1, steps) + 1):                              # first pass warms the tables
         t0 = time.perf_counter()
-        o.classify(pk, nthreads=cores)
+        o.classify(pk, offs, flags=flags, nthreads=cores)
         dt = time.perf_counter() - t0
-        best = max(best, pk.shape[0] / dt / 1e6)
-    sample = (f"{pk.shape[0]} packets of the same capture, {cores} threads, per-thread metrics maps (PERCPU)"
+        best = max(best, n_s / dt / 1e6)
+    sample = (f"{n_s} packets of the same capture, {cores} threads, per-thread metrics maps (PERCPU)"
               + ("; IP/CIDR extension rules are not evaluated by the reference (SURVEY R4)" if kind == "reference" else ""))
     return {"value": round(best, 2), "unit": "Mpackets/s", "cores": cores, "kind": kind, "sample": sample}
 
@@ -119,16 +141,14 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w, pk, spec = make_batch(args.workload, 0)
+    w, batch, spec = make_batch(args.workload, 0)
     t0 = time.perf_counter()
-    for _ in range(args.warmup):
-        pass
-    base = cpu_baseline(w, pk, steps=max(1, min(args.steps, 5)))
+    base = cpu_baseline(w, batch, steps=max(1, min(args.steps, 5)), name_stage=spec["layout"] == "varlen")
     line = {
         "metric": METRIC, "impl": "reference", "value": base["value"], "unit": "Mpackets/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(pk.shape[0] / base["value"] / 1e3, 3),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(batch_packets(batch) / base["value"] / 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"{spec['desc']}; bounded sample of {pk.shape[0]} packets per step on the host cores"},
+        "config": {"workload": f"{spec['desc']}; {base['sample']}"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "Mpackets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": round(time.perf_counter() - t0, 2),
@@ -151,14 +171,31 @@ def run_gpu(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    w, pk, spec = make_batch(args.workload, rank)
+    w, batch, spec = make_batch(args.workload, rank)
+    pk, offs = batch
+    varlen = offs is not None
+    gen = batch_packets(batch)
     n = spec["n"] if args.packets <= 0 else args.packets
+    reps = (n + gen - 1) // gen
+    n = reps * gen if varlen else n                                # varlen batches are tiled whole
     dev = torch.device("cuda", local)
-    d_unique = torch.from_numpy(pk).to(dev)
-    reps = (n + pk.shape[0] - 1) // pk.shape[0]
-    d_pk = d_unique.repeat(reps, 1)[:n].contiguous()
-    del d_unique
+    if varlen:
+        d_pk = torch.from_numpy(pk).to(dev).repeat(reps)
+        per = int(offs[-1])
+        o64 = torch.from_numpy(offs.astype(np.int64)).to(dev)
+        d_offs = torch.cat([o64[:-1] + k * per for k in range(reps)] + [o64[-1:] + (reps - 1) * per]).to(torch.int32)
+        total_bytes = int(d_pk.numel())
+        if (total_bytes >> 4) >= (1 << 32):
+            raise SystemExit("batch exceeds the 64 GiB reach of 16-byte offsets")
+        bytes_per_packet = total_bytes / n + 8
+    else:
+        d_unique = torch.from_numpy(pk).to(dev)
+        d_pk = d_unique.repeat(reps, 1)[:n].contiguous()
+        del d_unique
+        d_offs = None
+        bytes_per_packet = 68.0
     d_v = torch.empty(n, dtype=torch.int32, device=dev)
+    flags = 1 if varlen else 0                                     # CLK_F_NAME_STAGE on the varlen workload
 
     # metrics_map max_entries: 8x the reference default (common.h:173) so every key of the synthetic capture is counted;
     # keys beyond max_entries are dropped like the reference BPF_NOEXIST insert into a full map (--metrics-capacity)
@@ -174,12 +211,14 @@ def run_gpu(args) -> None:
     side = torch.cuda.Stream(device=dev)                           # the collective overlaps the next batch's kernel
     torch.cuda.set_stream(ts)
     st = ts.cuda_stream
-    flags = 0
 
     def step(ev_pair=None):
         if ev_pair:
             ev_pair[0].record(ts)
-        e.classify_slots_dev(d_pk.data_ptr(), 64, n, flags, d_v.data_ptr(), st)
+        if varlen:
+            e.classify_varlen_dev(d_pk.data_ptr(), d_offs.data_ptr(), n, flags, d_v.data_ptr(), st)
+        else:
+            e.classify_slots_dev(d_pk.data_ptr(), 64, n, flags, d_v.data_ptr(), st)
         if ev_pair:
             ev_pair[1].record(ts)
         if world > 1:                                              # the one collective: per-GPU counters over NVLink
@@ -214,18 +253,27 @@ def run_gpu(args) -> None:
     launches = e.stats().kernel_launches - launches0
 
     # ---- end to end: host buffers through the C-ABI (H2D + kernel + D2H inside the timed region) ----
-    n_e2e = min(n, 10_000_000)
-    h_pk = engine.pinned_empty(n_e2e * 64).reshape(n_e2e, 64)
-    h_pk[:] = np.resize(pk, (n_e2e, 64)) if pk.shape[0] < n_e2e else pk[:n_e2e]
+    e2e_reps = max(1, min(n, 10_000_000) // gen)
+    hp, ho = tile_host(batch, e2e_reps) if e2e_reps > 1 else batch
+    n_e2e = batch_packets((hp, ho))
+    h_pk = engine.pinned_empty(hp.size).reshape(hp.shape)
+    h_pk[...] = hp
     h_v = engine.pinned_empty(n_e2e * 4).view(np.uint32)
+    h2d_bytes = int(hp.size) + (int(ho.size) * 4 if varlen else 0)
+
+    def e2e_call():
+        if varlen:
+            e.classify_varlen(h_pk, ho, flags, out=h_v)
+        else:
+            e.classify_slots(h_pk, 64, flags, out=h_v)
     for _ in range(2):
-        e.classify_slots(h_pk, 64, flags, out=h_v)
+        e2e_call()
     if world > 1:
         dist.barrier()
     e2e_steps = max(2, min(args.steps, 5))
     tw0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e.classify_slots(h_pk, 64, flags, out=h_v)
+        e2e_call()
     e2e_ms = (time.perf_counter() - tw0) * 1e3 / e2e_steps
     clocks = sampler.stop() if sampler else None
 
@@ -238,25 +286,28 @@ def run_gpu(args) -> None:
         peak, how = peaks()
         ms_per_step = ms_total / args.steps
         value = world * n / ms_per_step / 1e3                     # Mpackets/s, whole job
-        achieved = n * BYTES_PER_PACKET / (kern_ms * 1e-3) / 1e9
-        prof = ROOT / "profiles" / "r01_traffic.json"
-        traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch") if prof.exists() else None
+        achieved = n * bytes_per_packet / (kern_ms * 1e-3) / 1e9
+        prof = ROOT / "profiles" / ("r01_traffic.json" if not varlen else "r01_varlen_traffic.json")
+        traffic = None
+        if prof.exists():                                          # ncu dram__bytes_{read,write}.sum of one launch, scaled to this launch's packets
+            pj = json.loads(prof.read_text())
+            traffic = round(pj["dram_bytes_per_launch"] * n / pj["packets_per_launch"])
         base = None
         if world == 1 and not args.no_cpu_baseline:
-            base = cpu_baseline(w, pk)
+            base = cpu_baseline(w, batch, name_stage=varlen)
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "Mpackets/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": spec["desc"], "packets_per_gpu_per_step": n, "rules": len(w.rules), "layout": "64 B slots",
-                       "l2_policy": "inputs_larger_than_l2 (640 MB per step vs 126 MB L2)",
+            "config": {"workload": spec["desc"], "packets_per_gpu_per_step": n, "rules": len(w.rules), "layout": "varlen (16 B aligned frames + u32 offsets)" if varlen else "64 B slots",
+                       "l2_policy": f"inputs_larger_than_l2 ({n * bytes_per_packet / 1e6:.0f} MB per step vs 126 MB L2)",
                        "parallelism": f"packet shards x{world}, tables replicated, 1 NCCL all-gather of counters per step" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "peak_source": how, "kernel": "clk::k_slots_fast", "kernel_ms": round(kern_ms, 4),
-                         "algorithmic_bytes_per_packet": BYTES_PER_PACKET},
-            "e2e": {"value": round(world * n_e2e / e2e_ms / 1e3, 1), "unit": "Mpackets/s", "h2d_bytes_per_step": n_e2e * 64,
+                         "traffic": traffic, "peak_source": how, "kernel": "clk::k_varlen_fast" if varlen else "clk::k_slots_fast", "kernel_ms": round(kern_ms, 4),
+                         "algorithmic_bytes_per_packet": round(bytes_per_packet, 2)},
+            "e2e": {"value": round(world * n_e2e / e2e_ms / 1e3, 1), "unit": "Mpackets/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": n_e2e * 4, "packets_per_step": n_e2e, "ms_per_step": round(e2e_ms, 3),
-                    "path": "clk_classify_slots (pinned host buffers, 3-stream chunked H2D/kernel/D2H)"},
+                    "path": ("clk_classify_varlen" if varlen else "clk_classify_slots") + " (pinned host buffers, 3-stream chunked H2D/kernel/D2H)"},
             "gpu_launches": int(launches), "clocks": clocks,
             "metrics": {"max_entries": args.metrics_capacity, "rows": int(e.counters().size), "dropped_increments": int(e.stats().metrics_dropped)},
         }

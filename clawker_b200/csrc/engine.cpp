@@ -698,6 +698,9 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
         if (offs16) {                                      // keep a chunk under 256 MiB of payload
             const uint64_t cap16 = (256ull << 20) / 16;
             while (cnt > 1 && (uint64_t)(offs16[done + cnt] - offs16[done]) > cap16) cnt /= 2;
+            // offsets must be monotonic (the kernel trusts them); checked per chunk so it overlaps earlier chunks' copies
+            for (uint64_t i = done; i < done + cnt; i++)
+                if (offs16[i + 1] < offs16[i]) return fail(e, CLK_EINVAL, "offs16 not monotonic at %llu", (unsigned long long)i);
         }
         int s = k % 3; cudaStream_t st = e->pipe[s];
         CUDA_TRY(e, cudaStreamSynchronize(st));            // buffers of this lane are free again
@@ -734,7 +737,6 @@ int clk_classify_slots(clk_engine *e, const uint8_t *pkts, uint32_t stride, uint
 int clk_classify_varlen(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, uint64_t n, uint32_t flags, uint32_t *verdicts)
 {
     if (!e || (n && (!pkts || !verdicts || !offs16))) return fail(e, CLK_EINVAL, "NULL buffer");
-    for (uint64_t i = 0; i < n; i++) if (offs16[i + 1] < offs16[i]) return fail(e, CLK_EINVAL, "offs16 not monotonic at %llu", (unsigned long long)i);
     return classify_host(e, pkts, offs16, 0, n, flags, verdicts);
 }
 

@@ -18,7 +18,7 @@ from .abi import (Cfg, ContainerConfig, DNSEntry, Endpoint, Cidr, Ports, Route, 
                   DNSUPD_DTYPE, EVENT_DTYPE, METRIC_DTYPE)
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libclawker_gpu.so"
+LIB_PATH = Path(os.environ["CLK_LIB"]) if os.environ.get("CLK_LIB") else PKG / "libclawker_gpu.so"
 
 
 class ClkError(RuntimeError):
