@@ -1,0 +1,208 @@
+// Package clkgpu is the cgo shim over libclawker_gpu.so (include/clawker_gpu.h).
+//
+// It contains no logic: every function marshals Go values into one clk_* call and maps the
+// negative return code to a Go error.  No Go pointer is retained by C across calls (cgo rule);
+// packet and verdict slices are pinned only for the duration of the call by cgo itself.
+package clkgpu
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -lclawker_gpu
+#include <stdlib.h>
+#include "clawker_gpu.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"unsafe"
+)
+
+// ErrKeyNotExist mirrors ebpf.ErrKeyNotExist (CLK_ENOENT).
+var ErrKeyNotExist = errors.New("key does not exist")
+
+// ErrMapFull mirrors the kernel's E2BIG on a full BPF hash map (CLK_E2BIG).
+var ErrMapFull = errors.New("map full")
+
+// Map ids (CLK_MAP_*).
+const (
+	MapContainer = C.CLK_MAP_CONTAINER
+	MapBypass    = C.CLK_MAP_BYPASS
+	MapDNSCache  = C.CLK_MAP_DNS_CACHE
+	MapRoute     = C.CLK_MAP_ROUTE
+	MapEndpoint  = C.CLK_MAP_ENDPOINT
+	MapEndpoint6 = C.CLK_MAP_ENDPOINT6
+	MapCIDR      = C.CLK_MAP_CIDR
+)
+
+// Classify flags (CLK_F_*).
+const (
+	FlagNameStage = C.CLK_F_NAME_STAGE
+	FlagNoMetrics = C.CLK_F_NO_METRICS
+)
+
+// Engine is one GPU's classifier instance.
+type Engine struct{ h *C.clk_engine }
+
+// Config mirrors clk_cfg; zero values select the reference's max_entries.
+type Config struct {
+	Device                                                         int
+	MaxContainers, MaxDNSCache, MaxRoutes, MaxMetrics, MaxCIDRs uint32
+}
+
+func (e *Engine) err(rc C.int) error {
+	switch rc {
+	case C.CLK_OK:
+		return nil
+	case C.CLK_ENOENT:
+		return ErrKeyNotExist
+	case C.CLK_E2BIG:
+		return fmt.Errorf("%w: %s", ErrMapFull, C.GoString(C.clk_last_error(e.h)))
+	default:
+		return fmt.Errorf("clawker_gpu: %s (%d)", C.GoString(C.clk_last_error(e.h)), int(rc))
+	}
+}
+
+// New creates the tables on one GPU (replaces loading and pinning the BPF objects).
+func New(cfg Config) (*Engine, error) {
+	c := C.clk_cfg{abi_version: C.CLK_ABI_VERSION, device: C.int32_t(cfg.Device),
+		max_containers: C.uint32_t(cfg.MaxContainers), max_dns_cache: C.uint32_t(cfg.MaxDNSCache),
+		max_routes: C.uint32_t(cfg.MaxRoutes), max_metrics: C.uint32_t(cfg.MaxMetrics), max_cidrs: C.uint32_t(cfg.MaxCIDRs)}
+	var h *C.clk_engine
+	if rc := C.clk_engine_create(&c, &h); rc != C.CLK_OK {
+		return nil, fmt.Errorf("clawker_gpu: %s (%d)", C.GoString(C.clk_last_error(nil)), int(rc))
+	}
+	return &Engine{h: h}, nil
+}
+
+// Close releases the engine.
+func (e *Engine) Close() error {
+	if e.h != nil {
+		C.clk_engine_destroy(e.h)
+		e.h = nil
+	}
+	return nil
+}
+
+// MapUpdate / MapDelete / MapLookup take the reference's row structs by pointer and size.
+func (e *Engine) MapUpdate(id int, key unsafe.Pointer, klen uintptr, val unsafe.Pointer, vlen uintptr) error {
+	return e.err(C.clk_map_update(e.h, C.int(id), key, C.size_t(klen), val, C.size_t(vlen)))
+}
+
+func (e *Engine) MapDelete(id int, key unsafe.Pointer, klen uintptr) error {
+	return e.err(C.clk_map_delete(e.h, C.int(id), key, C.size_t(klen)))
+}
+
+func (e *Engine) MapLookup(id int, key unsafe.Pointer, klen uintptr, val unsafe.Pointer, vlen uintptr) error {
+	return e.err(C.clk_map_lookup(e.h, C.int(id), key, C.size_t(klen), val, C.size_t(vlen)))
+}
+
+// Route is clk_route / ebpf.Route.
+type Route struct {
+	DomainHash uint32
+	DstPort    uint16
+	EnvoyPort  uint16
+}
+
+// RoutesReplace is Manager.SyncRoutes as one atomic replace.
+func (e *Engine) RoutesReplace(routes []Route) error {
+	var p *C.clk_route
+	if len(routes) > 0 {
+		p = (*C.clk_route)(unsafe.Pointer(&routes[0]))
+	}
+	return e.err(C.clk_routes_replace(e.h, p, C.uint32_t(len(routes))))
+}
+
+// DNSUpdate is dns_cache[ip] = {hash, now+ttl}; now == 0 means time.Now().
+func (e *Engine) DNSUpdate(ip, domainHash, ttl, now uint32) error {
+	return e.err(C.clk_dns_update(e.h, C.uint32_t(ip), C.uint32_t(domainHash), C.uint32_t(ttl), C.uint32_t(now)))
+}
+
+// DNSGC removes expired dns_cache rows and returns how many were cleared.
+func (e *Engine) DNSGC(now uint32) (int, error) {
+	rc := C.clk_dns_gc(e.h, C.uint32_t(now))
+	if rc < 0 {
+		return 0, e.err(rc)
+	}
+	return int(rc), nil
+}
+
+// Rule is config.EgressRule restricted to the fields on this path.
+type Rule struct {
+	Dst, Proto, Action string
+	Port               int
+}
+
+// RulesCompile replaces the zone table, the SNI table, the CIDR set and route_map from rules.
+func (e *Engine) RulesCompile(rules []Rule, egressPort, tcpPortBase int) (warnings uint32, err error) {
+	cr := make([]C.clk_rule, len(rules))
+	var frees []unsafe.Pointer
+	defer func() {
+		for _, p := range frees {
+			C.free(p)
+		}
+	}()
+	cs := func(s string) *C.char { p := C.CString(s); frees = append(frees, unsafe.Pointer(p)); return p }
+	for i, r := range rules {
+		cr[i] = C.clk_rule{dst: cs(r.Dst), proto: cs(r.Proto), port: C.int32_t(r.Port), action: cs(r.Action)}
+	}
+	ports := C.clk_ports{egress_port: C.int32_t(egressPort), tcp_port_base: C.int32_t(tcpPortBase)}
+	var p *C.clk_rule
+	if len(cr) > 0 {
+		p = &cr[0]
+	}
+	var w C.uint32_t
+	err = e.err(C.clk_rules_compile(e.h, p, C.uint32_t(len(cr)), &ports, &w))
+	return uint32(w), err
+}
+
+// Publish flips the table epoch: classification sees every change made so far.
+func (e *Engine) Publish() error { return e.err(C.clk_publish(e.h)) }
+
+// ClassifySlots classifies n = len(pkts)/stride frames laid out as fixed slots; verdicts must hold n words.
+func (e *Engine) ClassifySlots(pkts []byte, stride int, flags uint32, verdicts []uint32) error {
+	n := len(pkts) / stride
+	if n == 0 {
+		return nil
+	}
+	if len(verdicts) < n {
+		return errors.New("clawker_gpu: verdicts too short")
+	}
+	return e.err(C.clk_classify_slots(e.h, (*C.uint8_t)(unsafe.Pointer(&pkts[0])), C.uint32_t(stride), C.uint64_t(n),
+		C.uint32_t(flags), (*C.uint32_t)(unsafe.Pointer(&verdicts[0]))))
+}
+
+// ClassifyVarlen classifies len(offs16)-1 frames; frame i is bytes [16*offs16[i], 16*offs16[i+1]).
+func (e *Engine) ClassifyVarlen(pkts []byte, offs16 []uint32, flags uint32, verdicts []uint32) error {
+	n := len(offs16) - 1
+	if n <= 0 {
+		return nil
+	}
+	if len(verdicts) < n {
+		return errors.New("clawker_gpu: verdicts too short")
+	}
+	return e.err(C.clk_classify_varlen(e.h, (*C.uint8_t)(unsafe.Pointer(&pkts[0])), (*C.uint32_t)(unsafe.Pointer(&offs16[0])),
+		C.uint64_t(n), C.uint32_t(flags), (*C.uint32_t)(unsafe.Pointer(&verdicts[0]))))
+}
+
+// Metric is clk_metric: one metrics_map row summed over the GPU's counters.
+type Metric struct {
+	CgroupID   uint64
+	DomainHash uint32
+	DstPort    uint16
+	Action     uint8
+	_          uint8
+	Count      uint64
+}
+
+// CountersRead returns this GPU's metrics_map rows.
+func (e *Engine) CountersRead() ([]Metric, error) {
+	var n C.uint32_t
+	if err := e.err(C.clk_counters_read(e.h, nil, 0, &n)); err != nil || n == 0 {
+		return nil, err
+	}
+	out := make([]Metric, int(n))
+	err := e.err(C.clk_counters_read(e.h, (*C.clk_metric)(unsafe.Pointer(&out[0])), n, &n))
+	return out[:int(n)], err
+}
