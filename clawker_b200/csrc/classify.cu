@@ -94,7 +94,7 @@ struct Tabs {
 __device__ __forceinline__ bool dns_lookup(const DevTables &T, const Tabs &tb, uint32_t ip, uint32_t &hash)
 {
     if (ip == 0xffffffffu) { hash = T.dns_ffff_hash; return T.dns_ffff_present != 0; }
-    if (!tb.dns) return false;
+    if (!T.dns_b) return false;
     uint4 v = tb.dns[hash_a(ip) >> tb.dns_shift];
     if (v.x == ip) { hash = v.y; return true; }
     if (v.z == ip) { hash = v.w; return true; }
@@ -107,9 +107,9 @@ __device__ __forceinline__ bool dns_lookup(const DevTables &T, const Tabs &tb, u
 
 // route_map[{hash, port}] -> envoy_port.  Slot (lo, hi): hi = domain_hash, lo = dst_port << 16 | envoy_port;
 // empty = ~0 (the host rejects the one route whose key and value are all ones).
-__device__ __forceinline__ bool route_lookup(const Tabs &tb, uint32_t hash, uint32_t port, uint32_t &eport)
+__device__ __forceinline__ bool route_lookup(const DevTables &T, const Tabs &tb, uint32_t hash, uint32_t port, uint32_t &eport)
 {
-    if (!tb.route) return false;
+    if (!T.route_b) return false;
     const uint32_t f = route_fold(hash, port);
     uint4 v = tb.route[hash_a(f) >> tb.route_shift];
     uint32_t lo = 0xffffffffu;
@@ -148,9 +148,9 @@ __device__ __forceinline__ bool cidr_hit(const DevTables &T, const Tabs &tb, uin
 }
 
 // endpoint by IPv4 address -> EpRow index, or -1
-__device__ __forceinline__ int ep_find(const Tabs &tb, uint32_t ip)
+__device__ __forceinline__ int ep_find(const DevTables &T, const Tabs &tb, uint32_t ip)
 {
-    if (!tb.ep) return -1;
+    if (!T.ep_slots) return -1;
     uint32_t h = hash_a(ip) >> tb.ep_shift;
     #pragma unroll 1
     for (;;) {
@@ -202,7 +202,7 @@ __device__ __forceinline__ void decide_connect(const DevTables &T, const Tabs &t
     if (type == SOCK_DGRAM_) { emit(d, 0, port, CLK_ACTION_DENY); d.verdict = CLK_V_DENY; return; }
     uint32_t hash = 0, eport;
     if (dns_lookup(T, tb, ip, hash)) {
-        if (route_lookup(tb, hash, port, eport)) {
+        if (route_lookup(T, tb, hash, port, eport)) {
             d.verdict = CLK_V_REWRITE; d.new_ip = cfg->envoy_ip; d.new_port = eport;
             emit(d, hash, port, CLK_ACTION_ALLOW); return;
         }
@@ -283,7 +283,7 @@ __device__ __forceinline__ uint32_t make_word(const Decision &d, const clk_conta
 // ------------------------------------------------------------------------------------------------
 // metrics: warp match -> CTA shared-memory table (hot keys) -> device table (metric_inc common.h:190-210)
 // ------------------------------------------------------------------------------------------------
-#define MSLOTS 512u
+#define MSLOTS 512u              // default CTA aggregation table; k_slots_fast sizes its own from the shared memory left
 
 __device__ __forceinline__ uint32_t mhash(unsigned long long key)
 {
@@ -320,37 +320,67 @@ __device__ __forceinline__ unsigned int metric_global_add(const DevTables &T, un
     return metric_global_slow(T, key, cnt, h);
 }
 
-struct MetricAgg { unsigned long long *keys; unsigned int *counts; unsigned int dropped; };
+// Per-CTA aggregation state.  Increments are not applied by the (few, divergent) lanes that produce them:
+// each warp appends its distinct (key, count) pairs to a small log in shared memory and applies the log 32
+// entries at a time with every lane busy — first against the CTA's table of frequent keys, and only the misses
+// against the device table (so L2 atomics are issued 32 at a time instead of 1-3 at a time).
+#define MLOG_CAP 64u
+struct MetricAgg {
+    unsigned long long *keys; unsigned int *counts; uint32_t mask;     // CTA table (shared memory)
+    unsigned long long *log_keys; unsigned int *log_cnts; uint32_t log_n;   // this warp's log
+    unsigned int dropped;
+};
 
 // Two probes at most: keys that find a slot early (the frequent ones, by construction) stay in shared
-// memory for the CTA's lifetime; everything else goes straight to the device table.
+// memory for the CTA's lifetime; everything else goes to the device table.
 __device__ __forceinline__ void metric_cta_add(const DevTables &T, MetricAgg &ag, unsigned long long key, unsigned int cnt)
 {
-    uint32_t h = mhash(key) & (MSLOTS - 1);
+    uint32_t h = mhash(key) & ag.mask;
     #pragma unroll
     for (int p = 0; p < 2; p++) {
         unsigned long long cur = ag.keys[h];
         if (cur == 0ull) cur = atomicCAS(&ag.keys[h], 0ull, key);
         if (cur == 0ull || cur == key) { atomicAdd(&ag.counts[h], cnt); return; }
-        h = (h + 1) & (MSLOTS - 1);
+        h = (h + 1) & ag.mask;
     }
     ag.dropped += metric_global_add(T, key, cnt);
+}
+
+// Apply the first `take` (<= 32) log entries, one per lane.  All 32 lanes must call.
+__device__ __forceinline__ void metric_log_apply(const DevTables &T, MetricAgg &ag, uint32_t take)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long k = 0ull, k2 = 0ull; unsigned int c = 0u, c2 = 0u;
+    if (lane < take) { k = ag.log_keys[lane]; c = ag.log_cnts[lane]; }
+    if (lane + 32 < ag.log_n) { k2 = ag.log_keys[lane + 32]; c2 = ag.log_cnts[lane + 32]; }
+    __syncwarp();
+    if (lane + 32 < ag.log_n) { ag.log_keys[lane] = k2; ag.log_cnts[lane] = c2; }
+    ag.log_n -= take;
+    if (lane < take) metric_cta_add(T, ag, k, c);
+    __syncwarp();
 }
 
 // All 32 lanes must call (tail lanes with has == false).
 __device__ __forceinline__ void metric_warp_emit(const DevTables &T, MetricAgg &ag, bool has, unsigned long long key)
 {
-    unsigned m = __ballot_sync(0xffffffffu, has);
-    if (has) {
-        unsigned peers = __match_any_sync(m, key);
-        if ((int)(threadIdx.x & 31u) == __ffs(peers) - 1) metric_cta_add(T, ag, key, __popc(peers));
-    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    if (m == 0) return;
+    unsigned peers = 0;
+    if (has) peers = __match_any_sync(m, key);
+    const bool leader = has && (int)lane == __ffs(peers) - 1;
+    const unsigned lm = __ballot_sync(0xffffffffu, leader);
+    if (leader) { const uint32_t pos = ag.log_n + __popc(lm & ((1u << lane) - 1u)); ag.log_keys[pos] = key; ag.log_cnts[pos] = __popc(peers); }
+    ag.log_n += __popc(lm);
+    __syncwarp();
+    if (ag.log_n >= 32) metric_log_apply(T, ag, 32);
 }
 
 __device__ __forceinline__ void metric_cta_flush(const DevTables &T, MetricAgg &ag)
 {
+    if (ag.log_n) metric_log_apply(T, ag, ag.log_n);                    // log_n < 32 here
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < MSLOTS; i += blockDim.x)
+    for (uint32_t i = threadIdx.x; i <= ag.mask; i += blockDim.x)
         if (ag.keys[i]) ag.dropped += metric_global_add(T, ag.keys[i], ag.counts[i]);
     unsigned long long d = ag.dropped;                                  // one atomic per warp, and only if something was dropped
     for (int o = 16; o; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
@@ -384,9 +414,9 @@ __device__ __forceinline__ bool is_coredns(const DevTables &T, uint32_t ip)
 __device__ __forceinline__ void finish_v4(const DevTables &T, const Tabs &tb, uint32_t flags, Parsed &p,
                                           uint32_t src, uint32_t dst, uint32_t proto, uint32_t sport, uint32_t dport)
 {
-    int r = ep_find(tb, src);
+    int r = ep_find(T, tb, src);
     bool ingress = false;
-    if (r < 0 && proto == 17) { r = ep_find(tb, dst); ingress = r >= 0; }
+    if (r < 0 && proto == 17) { r = ep_find(T, tb, dst); ingress = r >= 0; }
     if (r < 0) {
         if (proto == 17 && sport == 53 && (flags & CLK_F_NAME_STAGE) && is_coredns(T, dst)) p.ans_candidate = true;
         return;
@@ -493,14 +523,15 @@ __device__ __noinline__ uint32_t generic_one(const DevTables &T, const Tabs &tb,
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up common to the kernels
 // ------------------------------------------------------------------------------------------------
-struct SmemLayout { uint32_t tiles, agg_keys, agg_counts, ep, soa, dns, route, pre, queue, bars, total; };
+struct SmemLayout { uint32_t tiles, agg_keys, agg_counts, mlog, ep, soa, dns, route, pre, queue, bars, total; };
 
-__host__ __device__ inline SmemLayout smem_layout(const DevTables &T, uint32_t tile_bytes, uint32_t queue_bytes, uint32_t n_bars)
+__host__ __device__ inline SmemLayout smem_layout(const DevTables &T, uint32_t tile_bytes, uint32_t queue_bytes, uint32_t n_bars, uint32_t agg_slots = MSLOTS, uint32_t n_warps = 8)
 {
     SmemLayout L; uint32_t o = 0;
     L.tiles = o; o += tile_bytes;                          // 1024 B aligned tiles first
-    L.agg_keys = o; o += MSLOTS * 8;
-    L.agg_counts = o; o += MSLOTS * 4;
+    L.agg_keys = o; o += agg_slots * 8;
+    L.agg_counts = o; o += agg_slots * 4;
+    L.mlog = o; o += n_warps * MLOG_CAP * 12;
     L.ep = o; o += (T.stage_ep_bytes + 15u) & ~15u;
     L.soa = o; o += (T.stage_soa_bytes + 15u) & ~15u;
     L.dns = o; o += (T.stage_dns_bytes + 15u) & ~15u;
@@ -514,11 +545,16 @@ __host__ __device__ inline SmemLayout smem_layout(const DevTables &T, uint32_t t
 
 // Stage the small tables into shared memory with 1-D TMA bulk copies (thread 0), zero the metric
 // aggregation table, and return the table views.  bars[n_bars] is used for the table copy.
-__device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, const SmemLayout &L, uint32_t n_bars, Tabs &tb, MetricAgg &ag)
+// kAllStaged: the host guarantees every small table is staged, so the views are shared-memory pointers
+// unconditionally (the compiler can then address them as shared: LDS with 32-bit addresses, fewer registers).
+template <bool kAllStaged>
+__device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, const SmemLayout &L, uint32_t n_bars, Tabs &tb, MetricAgg &ag, uint32_t agg_slots = MSLOTS)
 {
     ag.keys = (unsigned long long *)(smem + L.agg_keys);
-    ag.counts = (unsigned int *)(smem + L.agg_counts); ag.dropped = 0u;
-    for (uint32_t i = threadIdx.x; i < MSLOTS; i += blockDim.x) { ag.keys[i] = 0ull; ag.counts[i] = 0u; }
+    ag.counts = (unsigned int *)(smem + L.agg_counts); ag.dropped = 0u; ag.mask = agg_slots - 1;
+    ag.log_keys = (unsigned long long *)(smem + L.mlog) + (threadIdx.x >> 5) * MLOG_CAP;
+    ag.log_cnts = (unsigned int *)(smem + L.mlog + (blockDim.x >> 5) * MLOG_CAP * 8) + (threadIdx.x >> 5) * MLOG_CAP; ag.log_n = 0;
+    for (uint32_t i = threadIdx.x; i < agg_slots; i += blockDim.x) { ag.keys[i] = 0ull; ag.counts[i] = 0u; }
     uint64_t *bars = (uint64_t *)(smem + L.bars);
     tb.ep = T.ep_slots; tb.ep_mask = T.ep_mask; tb.ep_shift = T.ep_shift; tb.rowq = T.ep_rowq;
     tb.dns = T.dns_b; tb.dns_shift = T.dns_shift; tb.route = T.route_b; tb.route_shift = T.route_shift; tb.pre = T.cidr_pre;
@@ -535,6 +571,11 @@ __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, 
             if (T.stage_pre_bytes)   tma_load_1d(smem + L.pre, T.cidr_pre, T.stage_pre_bytes, &bars[n_bars]);
         }
         mbar_wait(&bars[n_bars], 0);
+        if (kAllStaged) {
+            tb.ep = (const uint2 *)(smem + L.ep); tb.rowq = (const uint4 *)(smem + L.soa); tb.dns = (const uint4 *)(smem + L.dns);
+            tb.route = (const uint4 *)(smem + L.route); tb.pre = (const uint32_t *)(smem + L.pre);
+            return;
+        }
         if (T.stage_ep_bytes)    tb.ep = (const uint2 *)(smem + L.ep);
         if (T.stage_soa_bytes)   tb.rowq = (const uint4 *)(smem + L.soa);
         if (T.stage_dns_bytes)   tb.dns = (const uint4 *)(smem + L.dns);
@@ -546,7 +587,7 @@ __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, 
 // ------------------------------------------------------------------------------------------------
 // kernel 1: 64-byte header slots through a TMA tile ring  (BASELINE configs 2, 4, 5)
 // ------------------------------------------------------------------------------------------------
-#define FAST_WARPS 16           // warps per CTA
+#define FAST_WARPS 32           // warps per CTA: one CTA per SM, so tables are staged once and the metric cache is large
 #define WTILE_BYTES 2048        // one warp tile: 32 slots x 64 B
 #define WQ_CAP 64               // per-warp queue of rare packets (drained 32 at a time)
 
@@ -570,9 +611,9 @@ __device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb
     const uint32_t sport = bswap16(q2x >> 16), dport = bswap16(q2y);
     const bool tcp = proto == 6, udp = proto == 17, raw = !tcp && !udp;
 
-    int r = ep_find(tb, src);
+    int r = ep_find(T, tb, src);
     bool ingress = false;
-    if (r < 0 && udp) { r = ep_find(tb, dst); ingress = r >= 0; }
+    if (r < 0 && udp) { r = ep_find(T, tb, dst); ingress = r >= 0; }
     word = 0; hm = false; mk = 0;
     if (r < 0) {                                                                 // no endpoint: no socket event ...
         if (kName && (flags & CLK_F_NAME_STAGE) && udp && sport == 53 && is_coredns(T, dst)) nm = NM_DNSA;   // ... but maybe an upstream answer reaching CoreDNS
@@ -609,7 +650,7 @@ __device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb
                     if (!(hp_port != 0 && port == hp_port)) { verdict = CLK_V_REWRITE; nip = envoy; nport = egress_port; metric = CLK_M_DENY; mp = port; }
                 } else {                                                                       // :386-409
                     uint32_t hash = 0, eport = egress_port;
-                    if (dns_lookup(T, tb, ip, hash)) route_lookup(tb, hash, port, eport);
+                    if (dns_lookup(T, tb, ip, hash)) route_lookup(T, tb, hash, port, eport);
                     verdict = CLK_V_REWRITE; nip = envoy; nport = eport; metric = CLK_M_ALLOW; mh = hash; mp = port;
                 }
             }
@@ -640,15 +681,15 @@ __device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb
 // The tile is copied to registers as soon as it lands and refilled immediately, which is why one
 // stage per warp already keeps the copy engine ahead of the ALU work.  Rare packets go to a per-warp
 // queue that is classified 32 at a time with all lanes converged.
-template <int kStages, bool kSwizzle, int kMinBlocks>
+template <int kStages, bool kSwizzle, int kMinBlocks, bool kAllStaged>
 __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(const __grid_constant__ DevTables T, const __grid_constant__ CUtensorMap map,
-                                                                const uint8_t *__restrict__ pkts, uint32_t stride,
+                                                                uint32_t *__restrict__ rare_q, uint32_t *__restrict__ rare_cnt, uint32_t agg_slots,
                                                                 unsigned long long n, uint32_t flags, uint32_t *__restrict__ verdicts)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemLayout L = smem_layout(T, FAST_WARPS * kStages * WTILE_BYTES, FAST_WARPS * WQ_CAP * 4, FAST_WARPS * kStages);
+    const SmemLayout L = smem_layout(T, FAST_WARPS * kStages * WTILE_BYTES, FAST_WARPS * WQ_CAP * 4, FAST_WARPS * kStages, agg_slots, FAST_WARPS);
     Tabs tb; MetricAgg ag;
-    cta_prologue(T, smem, L, FAST_WARPS * kStages, tb, ag);
+    cta_prologue<kAllStaged>(T, smem, L, FAST_WARPS * kStages, tb, ag, agg_slots);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint64_t *bars = (uint64_t *)(smem + L.bars) + warp * kStages;
     uint8_t *tiles = smem + L.tiles + warp * (kStages * WTILE_BYTES);
@@ -656,7 +697,6 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
     const uint32_t n_tiles = (uint32_t)((n + 31ull) >> 5);   // n < 2^31 on this path
     const uint32_t gw = blockIdx.x * FAST_WARPS + warp, W = gridDim.x * FAST_WARPS;
     const bool do_metrics = !(flags & CLK_F_NO_METRICS);
-    const uint32_t gflags = flags & ~CLK_F_NAME_STAGE;
     __syncthreads();                                         // tables staged, aggregation table zeroed, barriers initialised
 
     if (lane == 0) {
@@ -683,7 +723,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
         const uint32_t i = (t << 5) + lane;
         bool hm = false, slow = false; unsigned long long mk = 0; uint32_t w = 0;
         if (i < n) {
-            uint32_t nm; slow = !fast_classify<false>(T, tb, w3, q1, q2.x, q2.y, 0, 64, gflags, w, hm, mk, nm);
+            uint32_t nm; slow = !fast_classify<false>(T, tb, w3, q1, q2.x, q2.y, 0, 64, 0, w, hm, mk, nm);
             if (!slow) stg_stream(&verdicts[i], w);
         }
         const unsigned sm = __ballot_sync(0xffffffffu, slow);
@@ -693,25 +733,48 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
             __syncwarp();
         }
         if (do_metrics) metric_warp_emit(T, ag, hm, mk);
-        if (qn >= 32) {                                                      // 32 rare packets: classify them converged
-            const unsigned long long j = queue[lane];
+        if (qn >= 32) {                                                      // hand 32 rare packets to k_slots_rare
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(rare_cnt, 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            rare_q[base + lane] = queue[lane];
             const uint32_t carry = lane + 32 < qn ? queue[lane + 32] : 0;
-            bool hm2 = false; unsigned long long mk2 = 0;
-            stg_stream(&verdicts[j], generic_one(T, tb, pkts + j * stride, stride, gflags, hm2, mk2));
-            if (do_metrics) metric_warp_emit(T, ag, hm2, mk2);
             __syncwarp();
             if (lane + 32 < qn) queue[lane] = carry;
             qn -= 32;
             __syncwarp();
         }
     }
-    {                                                                        // leftovers (< 32)
-        bool hm2 = false; unsigned long long mk2 = 0;
-        if (lane < qn) {
-            const unsigned long long j = queue[lane];
-            stg_stream(&verdicts[j], generic_one(T, tb, pkts + j * stride, stride, gflags, hm2, mk2));
+    if (qn) {                                                                // leftovers (< 32)
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(rare_cnt, qn);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < qn) rare_q[base + lane] = queue[lane];
+    }
+    if (do_metrics) metric_cta_flush(T, ag);
+}
+
+// The rare frames of a slot batch (IPv6, IPv4 options, non-IP, malformed; ~2-3 % of a realistic mix), compacted by
+// k_slots_fast into rare_q: classified here by the generic path with all lanes busy.  Keeping this out of the main
+// kernel keeps that kernel free of calls (registers) and small (instruction cache).
+__global__ void __launch_bounds__(256) k_slots_rare(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts, uint32_t stride,
+                                                    const uint32_t *__restrict__ rare_q, const uint32_t *__restrict__ rare_cnt,
+                                                    uint32_t flags, uint32_t *__restrict__ verdicts)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
+    Tabs tb; MetricAgg ag;
+    cta_prologue<false>(T, smem, L, 0, tb, ag);
+    __syncthreads();
+    const bool do_metrics = !(flags & CLK_F_NO_METRICS);
+    const uint32_t cnt = *rare_cnt, cnt_round = (cnt + 31u) & ~31u, step = gridDim.x * blockDim.x;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt_round; k += step) {
+        bool hm = false; unsigned long long mk = 0;
+        if (k < cnt) {
+            const unsigned long long j = rare_q[k];
+            stg_stream(&verdicts[j], generic_one(T, tb, pkts + j * stride, stride, flags & ~CLK_F_NAME_STAGE, hm, mk));
         }
-        if (do_metrics) metric_warp_emit(T, ag, hm2, mk2);
+        if (do_metrics) metric_warp_emit(T, ag, hm, mk);
     }
     if (do_metrics) metric_cta_flush(T, ag);
 }
@@ -759,9 +822,9 @@ __global__ void __launch_bounds__(VL_WARPS * 32, 2) k_varlen_fast(const __grid_c
                                                                   uint32_t flags, uint32_t *__restrict__ verdicts)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemLayout L = smem_layout(T, 0, VL_WARPS * VL_QUEUES * VL_QCAP * 8, 0);
+    const SmemLayout L = smem_layout(T, 0, VL_WARPS * VL_QUEUES * VL_QCAP * 8, 0, MSLOTS, VL_WARPS);
     Tabs tb; MetricAgg ag;
-    cta_prologue(T, smem, L, 0, tb, ag);
+    cta_prologue<false>(T, smem, L, 0, tb, ag);
     __syncthreads();
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint2 *queue = (uint2 *)(smem + L.queue) + warp * (VL_QUEUES * VL_QCAP);      // entry: {packet index, phase-A word}
@@ -833,9 +896,9 @@ __global__ void __launch_bounds__(256) k_generic(const __grid_constant__ DevTabl
                                                  uint32_t flags, uint32_t *__restrict__ verdicts)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemLayout L = smem_layout(T, 0, 0, 0);
+    const SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
     Tabs tb; MetricAgg ag;
-    cta_prologue(T, smem, L, 0, tb, ag);
+    cta_prologue<false>(T, smem, L, 0, tb, ag);
     __syncthreads();
     const bool do_metrics = !(flags & CLK_F_NO_METRICS);
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
@@ -860,9 +923,9 @@ __global__ void __launch_bounds__(256) k_events(const __grid_constant__ DevTable
                                                 unsigned long long n, uint32_t flags, uint32_t *__restrict__ verdicts)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemLayout L = smem_layout(T, 0, 0, 0);
+    const SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
     Tabs tb; MetricAgg ag;
-    cta_prologue(T, smem, L, 0, tb, ag);
+    cta_prologue<false>(T, smem, L, 0, tb, ag);
     __syncthreads();
     const bool do_metrics = !(flags & CLK_F_NO_METRICS);
     const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
@@ -1022,29 +1085,44 @@ static cudaError_t occupancy_grid(K kernel, int threads, size_t smem, int *grid)
     return cudaSuccess;
 }
 
-template <int kStages, bool kSwizzle, int kMinBlocks>
+template <int kStages, bool kSwizzle, int kMinBlocks, bool kAllStaged>
 static const char *launch_fast(const DevTables &T, const CUtensorMap &map, const void *d_pkts, uint32_t stride, unsigned long long n,
-                               uint32_t flags, uint32_t *d_verdicts, cudaStream_t st, LaunchInfo *info)
+                               uint32_t flags, uint32_t *d_verdicts, cudaStream_t st, uint32_t *rare_q, uint32_t *rare_cnt, LaunchInfo *info)
 {
     int grid = 0; cudaError_t e;
-    SmemLayout L = smem_layout(T, FAST_WARPS * kStages * WTILE_BYTES, FAST_WARPS * WQ_CAP * 4, FAST_WARPS * kStages);
-    if ((e = occupancy_grid(k_slots_fast<kStages, kSwizzle, kMinBlocks>, FAST_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
+    // metric cache: the largest power of two that still fits kMinBlocks CTAs per SM (227 KiB per SM, 1 KiB reserved per CTA)
+    uint32_t agg_slots = 512;
+    const uint32_t budget = (227u * 1024u) / kMinBlocks - 1024u;
+    while (agg_slots < 2048 && smem_layout(T, FAST_WARPS * kStages * WTILE_BYTES, FAST_WARPS * WQ_CAP * 4, FAST_WARPS * kStages, agg_slots * 2, FAST_WARPS).total <= budget) agg_slots *= 2;
+    if (const char *s = getenv("CLK_AGG_SLOTS")) { uint32_t v = (uint32_t)atoi(s); if (v >= 64 && (v & (v - 1)) == 0) agg_slots = v; }
+    SmemLayout L = smem_layout(T, FAST_WARPS * kStages * WTILE_BYTES, FAST_WARPS * WQ_CAP * 4, FAST_WARPS * kStages, agg_slots, FAST_WARPS);
+    if ((e = occupancy_grid(k_slots_fast<kStages, kSwizzle, kMinBlocks, kAllStaged>, FAST_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long n_cta = ((n + 31) / 32 + FAST_WARPS - 1) / FAST_WARPS;
     if ((unsigned long long)grid > n_cta) grid = (int)n_cta;
-    k_slots_fast<kStages, kSwizzle, kMinBlocks><<<grid, FAST_WARPS * 32, L.total, st>>>(T, map, (const uint8_t *)d_pkts, stride, n, flags, d_verdicts);
+    if ((e = cudaMemsetAsync(rare_cnt, 0, 4, st)) != cudaSuccess) return cudaGetErrorString(e);
+    k_slots_fast<kStages, kSwizzle, kMinBlocks, kAllStaged><<<grid, FAST_WARPS * 32, L.total, st>>>(T, map, rare_q, rare_cnt, agg_slots, n, flags, d_verdicts);
     if (info) { info->grid = grid; info->block = FAST_WARPS * 32; info->smem = L.total; }
+    if ((e = cudaGetLastError()) != cudaSuccess) return cudaGetErrorString(e);
+    // rare frames: one packet per thread (the loads are DRAM-latency bound, so width is what matters); tables stay in L2
+    DevTables Tr = T; Tr.stage_ep_bytes = Tr.stage_soa_bytes = Tr.stage_dns_bytes = Tr.stage_route_bytes = Tr.stage_pre_bytes = 0;
+    SmemLayout Lr = smem_layout(Tr, 0, 0, 0, MSLOTS, 8);
+    if ((e = cudaFuncSetAttribute(k_slots_rare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lr.total)) != cudaSuccess) return cudaGetErrorString(e);
+    unsigned long long rare_blocks = (n / 16 + 255) / 256;                       // sized for ~6 % rare frames; the kernel loops beyond that
+    if (rare_blocks < 1) rare_blocks = 1;
+    if (rare_blocks > (unsigned long long)sm_count() * 8) rare_blocks = (unsigned long long)sm_count() * 8;
+    k_slots_rare<<<(int)rare_blocks, 256, Lr.total, st>>>(Tr, (const uint8_t *)d_pkts, stride, rare_q, rare_cnt, flags, d_verdicts);
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride, unsigned long long n, uint32_t flags,
-                         uint32_t *d_verdicts, cudaStream_t st, int loader, int stages, LaunchInfo *info)
+                         uint32_t *d_verdicts, cudaStream_t st, int loader, int stages, uint32_t *rare_q, uint32_t *rare_cnt, LaunchInfo *info)
 {
     if (n == 0) return nullptr;
     cudaError_t e;
     int grid = 0;
     if (loader == LOADER_DIRECT || (flags & CLK_F_NAME_STAGE) || n >= 0x7fffffffull || stride > 0xffff0u) {
-        SmemLayout L = smem_layout(T, 0, 0, 0);
+        SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
         if ((e = occupancy_grid(k_generic<false>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
         unsigned long long need = (n + 255) / 256; if ((unsigned long long)grid > need) grid = (int)need;
         k_generic<false><<<grid, 256, L.total, st>>>(T, (const uint8_t *)d_pkts, nullptr, stride, n, flags, d_verdicts);
@@ -1063,13 +1141,18 @@ const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride
                      loader == LOADER_TMA_SW64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed";
-#define FAST_ARGS T, map, d_pkts, stride, n, flags, d_verdicts, st, info
+#define FAST_ARGS T, map, d_pkts, stride, n, flags, d_verdicts, st, rare_q, rare_cnt, info
     const int minb = stages >> 4; stages &= 15;              // stages | minblocks << 4 (tuning knob CLK_STAGES / CLK_MINB)
-    if (loader != LOADER_TMA_SW64) return launch_fast<2, false, 2>(FAST_ARGS);
-    if (minb >= 3) return stages <= 1 ? launch_fast<1, true, 3>(FAST_ARGS) : launch_fast<2, true, 3>(FAST_ARGS);
-    if (stages <= 1) return launch_fast<1, true, 2>(FAST_ARGS);
-    if (stages == 2) return launch_fast<2, true, 2>(FAST_ARGS);
-    return launch_fast<3, true, 2>(FAST_ARGS);
+    // every small table present is staged (and at least the endpoint table exists) -> shared-memory specialisation
+    const bool all_staged = T.stage_ep_bytes && T.stage_soa_bytes && (!T.dns_b || T.stage_dns_bytes) && (!T.route_b || T.stage_route_bytes) &&
+                            (!T.n_cidr || T.stage_pre_bytes);
+    if (loader != LOADER_TMA_SW64) return launch_fast<2, false, 1, false>(FAST_ARGS);
+    if (all_staged) {
+        if (minb >= 2) return launch_fast<1, true, 2, true>(FAST_ARGS);                 // 2 x 1024 threads per SM (<= 32 registers)
+        return stages <= 1 ? launch_fast<1, true, 1, true>(FAST_ARGS) : launch_fast<2, true, 1, true>(FAST_ARGS);
+    }
+    if (stages <= 1) return launch_fast<1, true, 1, false>(FAST_ARGS);
+    return launch_fast<2, true, 1, false>(FAST_ARGS);
 #undef FAST_ARGS
 }
 
@@ -1079,7 +1162,7 @@ const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t
     if (n == 0) return nullptr;
     int grid = 0; cudaError_t e;
     if (n < 0x7fffffffull && !getenv("CLK_VARLEN_GENERIC")) {
-        SmemLayout L = smem_layout(T, 0, VL_WARPS * VL_QUEUES * VL_QCAP * 8, 0);
+        SmemLayout L = smem_layout(T, 0, VL_WARPS * VL_QUEUES * VL_QCAP * 8, 0, MSLOTS, VL_WARPS);
         if ((e = occupancy_grid(k_varlen_fast, VL_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
         unsigned long long need = ((n + 31) / 32 + VL_WARPS - 1) / VL_WARPS; if ((unsigned long long)grid > need) grid = (int)need;
         k_varlen_fast<<<grid, VL_WARPS * 32, L.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, n, flags, d_verdicts);
@@ -1087,7 +1170,7 @@ const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t
         e = cudaGetLastError();
         return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
     }
-    SmemLayout L = smem_layout(T, 0, 0, 0);
+    SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
     if ((e = occupancy_grid(k_generic<true>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long need = (n + 255) / 256; if ((unsigned long long)grid > need) grid = (int)need;
     k_generic<true><<<grid, 256, L.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, 0, n, flags, d_verdicts);
@@ -1101,7 +1184,7 @@ const char *launch_events(const DevTables &T, const clk_event *d_ev, unsigned lo
 {
     if (n == 0) return nullptr;
     int grid = 0; cudaError_t e;
-    SmemLayout L = smem_layout(T, 0, 0, 0);
+    SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
     if ((e = occupancy_grid(k_events, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long need = (n + 255) / 256; if ((unsigned long long)grid > need) grid = (int)need;
     k_events<<<grid, 256, L.total, st>>>(T, d_ev, n, flags, d_verdicts);

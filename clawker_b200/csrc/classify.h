@@ -12,7 +12,7 @@ struct LaunchInfo { uint32_t grid, block, smem; };
 
 // All launchers enqueue on `st` and return nullptr on success or a static error string.
 const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride, unsigned long long n, uint32_t flags,
-                         uint32_t *d_verdicts, cudaStream_t st, int loader, int stages, LaunchInfo *info);
+                         uint32_t *d_verdicts, cudaStream_t st, int loader, int stages, uint32_t *rare_q, uint32_t *rare_cnt, LaunchInfo *info);
 const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n, uint32_t flags,
                           uint32_t *d_verdicts, cudaStream_t st, LaunchInfo *info);
 const char *launch_events(const DevTables &T, const clk_event *d_ev, unsigned long long n, uint32_t flags, uint32_t *d_verdicts,

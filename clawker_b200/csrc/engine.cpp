@@ -89,6 +89,7 @@ struct clk_engine {
     DevTables T;                                                         // active snapshot
     DevBuf m_keys, m_counts, m_dropped;      // this GPU's metrics_map (kernels write)
     DevBuf g_keys, g_counts, g_dropped;      // merged view after the all-gather (clk_counters_import)
+    DevBuf work_rare[4];                       // rare-frame queues: [0..2] host pipeline lanes, [3] the *_dev entry
     DevBuf work_pkts[3], work_offs[3], work_verd[3], scan_sums, scan_pos, scan_total, upd_out, ctr_block;
     clk_stats stats;
     int loader = LOADER_TMA_SW64;
@@ -449,6 +450,7 @@ void clk_engine_destroy(clk_engine *e)
         cudaDeviceSynchronize();
         e->snap[0].release(); e->snap[1].release();
         for (DevBuf *b : { &e->m_keys, &e->m_counts, &e->m_dropped, &e->g_keys, &e->g_counts, &e->g_dropped, &e->scan_sums, &e->scan_pos, &e->scan_total, &e->upd_out, &e->ctr_block }) b->release();
+        for (int i = 0; i < 4; i++) e->work_rare[i].release();
         for (int i = 0; i < 3; i++) { e->work_pkts[i].release(); e->work_offs[i].release(); e->work_verd[i].release(); if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]); }
         if (e->ev0) cudaEventDestroy(e->ev0);
         if (e->ev1) cudaEventDestroy(e->ev1);
@@ -665,7 +667,9 @@ int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, u
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     LaunchInfo li = { 0, 0, 0 };
     cudaEventRecord(e->ev0, st);
-    const char *err = launch_slots(e->T, d_pkts, stride, n, flags, (uint32_t *)d_verdicts, st, e->loader, e->stages, &li);
+    CUDA_TRY(e, e->work_rare[3].ensure((n + 1) * 4));          // grows only when a larger batch arrives
+    const char *err = launch_slots(e->T, d_pkts, stride, n, flags, (uint32_t *)d_verdicts, st, e->loader, e->stages,
+                                   (uint32_t *)e->work_rare[3].p + 1, (uint32_t *)e->work_rare[3].p, &li);
     cudaEventRecord(e->ev1, st);
     return finish_launch(e, err, li);
 }
@@ -717,7 +721,9 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
         } else {
             CUDA_TRY(e, e->work_pkts[s].ensure(cnt * stride));
             CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + done * stride, cnt * stride, cudaMemcpyHostToDevice, st));
-            err = launch_slots(e->T, e->work_pkts[s].p, stride, cnt, flags, (uint32_t *)e->work_verd[s].p, st, e->loader, e->stages, &li);
+            CUDA_TRY(e, e->work_rare[s].ensure((cnt + 1) * 4));
+            err = launch_slots(e->T, e->work_pkts[s].p, stride, cnt, flags, (uint32_t *)e->work_verd[s].p, st, e->loader, e->stages,
+                               (uint32_t *)e->work_rare[s].p + 1, (uint32_t *)e->work_rare[s].p, &li);
         }
         rc = finish_launch(e, err, li); if (rc) return rc;
         CUDA_TRY(e, cudaMemcpyAsync(verdicts + done, e->work_verd[s].p, cnt * 4, cudaMemcpyDeviceToHost, st));

@@ -10,8 +10,8 @@ d = torch.from_numpy(pk).cuda()
 d = d.repeat((n + pk.shape[0] - 1) // pk.shape[0], 1)[:n].contiguous()
 v = torch.empty(n, dtype=torch.int32, device="cuda")
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); st = ts.cuda_stream
-for stages, minb, flags in itertools.product((1, 2, 3), (2, 3), (0, 2)):
-    if stages == 3 and minb == 3: continue
+for stages, minb, flags in itertools.product((1, 2), (1, 2), (0, 2)):
+    if stages == 2 and minb == 2: continue
     os.environ["CLK_STAGES"] = str(stages); os.environ["CLK_MINB"] = str(minb)
     e = engine.Engine(device=0, max_metrics=1 << 20)
     e.load_tables(w.tables); e.compile_rules(w.rules); e.publish()
