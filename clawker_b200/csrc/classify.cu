@@ -80,6 +80,7 @@ struct Tabs {
     const uint4    *dns;   uint32_t dns_shift;
     const uint4    *route; uint32_t route_shift;
     const uint32_t *pre;                       // CIDR /16 prefilter (null when there are no CIDR rules)
+    const Ep6Key   *ep6;                       // IPv6 endpoints
 };
 
 #define SOCK_STREAM_ 1u
@@ -160,13 +161,18 @@ __device__ __forceinline__ int ep_find(const DevTables &T, const Tabs &tb, uint3
         h = (h + 1) & tb.ep_mask;
     }
 }
-__device__ __forceinline__ int ep_find6(const DevTables &T, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3)
+__device__ __forceinline__ int ep_find6(const DevTables &T, const Tabs &tb, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3)
 {
-    for (uint32_t i = 0; i < T.n_ep6; i++) {
-        const Ep6Key *k = &T.ep6[i];
-        if (k->a[0] == a0 && k->a[1] == a1 && k->a[2] == a2 && k->a[3] == a3) return (int)k->row;
+    if (!T.ep6) return -1;
+    uint32_t h = hash_a(a0 ^ a1 ^ a2 ^ a3) >> T.ep6_shift;
+    #pragma unroll 1
+    for (;;) {
+        const uint4 k = *(const uint4 *)&tb.ep6[h];
+        const uint32_t row = tb.ep6[h].row;
+        if (row == 0xffffffffu) return -1;
+        if (k.x == a0 && k.y == a1 && k.z == a2 && k.w == a3) return (int)row;
+        h = (h + 1) & T.ep6_mask;
     }
-    return -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -473,9 +479,9 @@ __device__ __forceinline__ void parse_headers(const DevTables &T, const Tabs &tb
                  s2 = __byte_perm(q1.w, q2.x, 0x5432), s3 = __byte_perm(q2.x, q2.y, 0x5432);
         uint32_t d0 = __byte_perm(q2.y, q2.z, 0x5432), d1 = __byte_perm(q2.z, q2.w, 0x5432),
                  d2 = __byte_perm(q2.w, q3.x, 0x5432), d3 = __byte_perm(q3.x, q3.y, 0x5432);
-        int r = ep_find6(T, s0, s1, s2, s3);
+        int r = ep_find6(T, tb, s0, s1, s2, s3);
         bool ingress = false;
-        if (r < 0 && proto == 17) { r = ep_find6(T, d0, d1, d2, d3); ingress = r >= 0; }
+        if (r < 0 && proto == 17) { r = ep_find6(T, tb, d0, d1, d2, d3); ingress = r >= 0; }
         p.proto = proto; p.l4off = 54; p.end = end; p.v6 = true;
         if (r < 0) return;
         p.row = &T.ep_rows[r]; p.ingress = ingress;
@@ -523,7 +529,7 @@ __device__ __noinline__ uint32_t generic_one(const DevTables &T, const Tabs &tb,
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up common to the kernels
 // ------------------------------------------------------------------------------------------------
-struct SmemLayout { uint32_t tiles, agg_keys, agg_counts, mlog, ep, soa, dns, route, pre, queue, bars, total; };
+struct SmemLayout { uint32_t tiles, agg_keys, agg_counts, mlog, ep, soa, dns, route, pre, ep6, queue, bars, total; };
 
 __host__ __device__ inline SmemLayout smem_layout(const DevTables &T, uint32_t tile_bytes, uint32_t queue_bytes, uint32_t n_bars, uint32_t agg_slots = MSLOTS, uint32_t n_warps = 8)
 {
@@ -537,6 +543,7 @@ __host__ __device__ inline SmemLayout smem_layout(const DevTables &T, uint32_t t
     L.dns = o; o += (T.stage_dns_bytes + 15u) & ~15u;
     L.route = o; o += (T.stage_route_bytes + 15u) & ~15u;
     L.pre = o; o += (T.stage_pre_bytes + 15u) & ~15u;
+    L.ep6 = o; o += (T.stage_ep6_bytes + 15u) & ~15u;
     L.queue = o; o += queue_bytes;
     L.bars = o; o += (n_bars + 1) * 8;
     L.total = o;
@@ -557,8 +564,8 @@ __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, 
     for (uint32_t i = threadIdx.x; i < agg_slots; i += blockDim.x) { ag.keys[i] = 0ull; ag.counts[i] = 0u; }
     uint64_t *bars = (uint64_t *)(smem + L.bars);
     tb.ep = T.ep_slots; tb.ep_mask = T.ep_mask; tb.ep_shift = T.ep_shift; tb.rowq = T.ep_rowq;
-    tb.dns = T.dns_b; tb.dns_shift = T.dns_shift; tb.route = T.route_b; tb.route_shift = T.route_shift; tb.pre = T.cidr_pre;
-    const uint32_t nb = T.stage_ep_bytes + T.stage_soa_bytes + T.stage_dns_bytes + T.stage_route_bytes + T.stage_pre_bytes;
+    tb.dns = T.dns_b; tb.dns_shift = T.dns_shift; tb.route = T.route_b; tb.route_shift = T.route_shift; tb.pre = T.cidr_pre; tb.ep6 = T.ep6;
+    const uint32_t nb = T.stage_ep_bytes + T.stage_soa_bytes + T.stage_dns_bytes + T.stage_route_bytes + T.stage_pre_bytes + T.stage_ep6_bytes;
     if (threadIdx.x == 0) { for (uint32_t i = 0; i <= n_bars; i++) mbar_init(&bars[i], 1); fence_mbar_init(); }
     __syncthreads();
     if (nb) {
@@ -569,11 +576,12 @@ __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, 
             if (T.stage_dns_bytes)   tma_load_1d(smem + L.dns, T.dns_b, T.stage_dns_bytes, &bars[n_bars]);
             if (T.stage_route_bytes) tma_load_1d(smem + L.route, T.route_b, T.stage_route_bytes, &bars[n_bars]);
             if (T.stage_pre_bytes)   tma_load_1d(smem + L.pre, T.cidr_pre, T.stage_pre_bytes, &bars[n_bars]);
+            if (T.stage_ep6_bytes)   tma_load_1d(smem + L.ep6, T.ep6, T.stage_ep6_bytes, &bars[n_bars]);
         }
         mbar_wait(&bars[n_bars], 0);
         if (kAllStaged) {
             tb.ep = (const uint2 *)(smem + L.ep); tb.rowq = (const uint4 *)(smem + L.soa); tb.dns = (const uint4 *)(smem + L.dns);
-            tb.route = (const uint4 *)(smem + L.route); tb.pre = (const uint32_t *)(smem + L.pre);
+            tb.route = (const uint4 *)(smem + L.route); tb.pre = (const uint32_t *)(smem + L.pre); tb.ep6 = (const Ep6Key *)(smem + L.ep6);
             return;
         }
         if (T.stage_ep_bytes)    tb.ep = (const uint2 *)(smem + L.ep);
@@ -581,6 +589,7 @@ __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, 
         if (T.stage_dns_bytes)   tb.dns = (const uint4 *)(smem + L.dns);
         if (T.stage_route_bytes) tb.route = (const uint4 *)(smem + L.route);
         if (T.stage_pre_bytes)   tb.pre = (const uint32_t *)(smem + L.pre);
+        if (T.stage_ep6_bytes)   tb.ep6 = (const Ep6Key *)(smem + L.ep6);
     }
 }
 
@@ -605,7 +614,11 @@ __device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb
 {
     nm = NM_NONE;
     // Ethernet II + IPv4 without options, not a later fragment
-    if ((w3 & 0x00ffffffu) != 0x00450008u || (q1.y & 0xff1fu) != 0) return false;
+    if ((w3 & 0x00ffffffu) != 0x00450008u || (q1.y & 0xff1fu) != 0) {
+        const uint32_t et = w3 & 0xffffu;                                        // ethertype, network order in the low half
+        if (et != 0x0008u && et != 0xDD86u) { word = 0; hm = false; mk = 0; nm = NM_NONE; return true; }   // not IP: no socket event
+        return false;
+    }
     const uint32_t proto = q1.y >> 24;
     const uint32_t src = __byte_perm(q1.z, q1.w, 0x5432), dst = __byte_perm(q1.w, q2x, 0x5432);
     const uint32_t sport = bswap16(q2x >> 16), dport = bswap16(q2y);
@@ -683,6 +696,7 @@ __device__ __forceinline__ bool fast_classify(const DevTables &T, const Tabs &tb
 // queue that is classified 32 at a time with all lanes converged.
 template <int kStages, bool kSwizzle, int kMinBlocks, bool kAllStaged>
 __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(const __grid_constant__ DevTables T, const __grid_constant__ CUtensorMap map,
+                                                                const uint8_t *__restrict__ pkts, uint32_t stride,
                                                                 uint32_t *__restrict__ rare_q, uint32_t *__restrict__ rare_cnt, uint32_t agg_slots,
                                                                 unsigned long long n, uint32_t flags, uint32_t *__restrict__ verdicts)
 {
@@ -751,30 +765,28 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
         base = __shfl_sync(0xffffffffu, base, 0);
         if (lane < qn) rare_q[base + lane] = queue[lane];
     }
-    if (do_metrics) metric_cta_flush(T, ag);
-}
-
-// The rare frames of a slot batch (IPv6, IPv4 options, non-IP, malformed; ~2-3 % of a realistic mix), compacted by
-// k_slots_fast into rare_q: classified here by the generic path with all lanes busy.  Keeping this out of the main
-// kernel keeps that kernel free of calls (registers) and small (instruction cache).
-__global__ void __launch_bounds__(256) k_slots_rare(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts, uint32_t stride,
-                                                    const uint32_t *__restrict__ rare_q, const uint32_t *__restrict__ rare_cnt,
-                                                    uint32_t flags, uint32_t *__restrict__ verdicts)
-{
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
-    Tabs tb; MetricAgg ag;
-    cta_prologue<false>(T, smem, L, 0, tb, ag);
+    // ---- rare frames (IPv6, IPv4 options, malformed; a few % of a realistic mix) ------------------------------
+    // Every CTA of this launch is resident (grid = SMs x occupancy), so a counter barrier across the grid is safe.
+    // After it the whole grid walks the compacted queue with the generic path, all lanes busy, tables and the
+    // metric cache still in shared memory — no second launch, no second prologue / flush.
     __syncthreads();
-    const bool do_metrics = !(flags & CLK_F_NO_METRICS);
-    const uint32_t cnt = *rare_cnt, cnt_round = (cnt + 31u) & ~31u, step = gridDim.x * blockDim.x;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt_round; k += step) {
-        bool hm = false; unsigned long long mk = 0;
-        if (k < cnt) {
-            const unsigned long long j = rare_q[k];
-            stg_stream(&verdicts[j], generic_one(T, tb, pkts + j * stride, stride, flags & ~CLK_F_NAME_STAGE, hm, mk));
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(&rare_cnt[1], 1u);
+        while (*(volatile uint32_t *)&rare_cnt[1] < gridDim.x) { }
+        __threadfence();
+    }
+    __syncthreads();
+    {
+        const uint32_t cnt = *(volatile uint32_t *)&rare_cnt[0], cnt_round = (cnt + 31u) & ~31u;
+        for (uint32_t k = (gw << 5) + lane; k < cnt_round; k += W << 5) {
+            bool hm = false; unsigned long long mk = 0;
+            if (k < cnt) {
+                const unsigned long long j = rare_q[k];
+                stg_stream(&verdicts[j], generic_one(T, tb, pkts + j * stride, stride, flags & ~CLK_F_NAME_STAGE, hm, mk));
+            }
+            if (do_metrics) metric_warp_emit(T, ag, hm, mk);
         }
-        if (do_metrics) metric_warp_emit(T, ag, hm, mk);
     }
     if (do_metrics) metric_cta_flush(T, ag);
 }
@@ -1099,18 +1111,9 @@ static const char *launch_fast(const DevTables &T, const CUtensorMap &map, const
     if ((e = occupancy_grid(k_slots_fast<kStages, kSwizzle, kMinBlocks, kAllStaged>, FAST_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long n_cta = ((n + 31) / 32 + FAST_WARPS - 1) / FAST_WARPS;
     if ((unsigned long long)grid > n_cta) grid = (int)n_cta;
-    if ((e = cudaMemsetAsync(rare_cnt, 0, 4, st)) != cudaSuccess) return cudaGetErrorString(e);
-    k_slots_fast<kStages, kSwizzle, kMinBlocks, kAllStaged><<<grid, FAST_WARPS * 32, L.total, st>>>(T, map, rare_q, rare_cnt, agg_slots, n, flags, d_verdicts);
+    if ((e = cudaMemsetAsync(rare_cnt, 0, 8, st)) != cudaSuccess) return cudaGetErrorString(e);     // [0] queue length, [1] grid barrier
+    k_slots_fast<kStages, kSwizzle, kMinBlocks, kAllStaged><<<grid, FAST_WARPS * 32, L.total, st>>>(T, map, (const uint8_t *)d_pkts, stride, rare_q, rare_cnt, agg_slots, n, flags, d_verdicts);
     if (info) { info->grid = grid; info->block = FAST_WARPS * 32; info->smem = L.total; }
-    if ((e = cudaGetLastError()) != cudaSuccess) return cudaGetErrorString(e);
-    // rare frames: one packet per thread (the loads are DRAM-latency bound, so width is what matters); tables stay in L2
-    DevTables Tr = T; Tr.stage_ep_bytes = Tr.stage_soa_bytes = Tr.stage_dns_bytes = Tr.stage_route_bytes = Tr.stage_pre_bytes = 0;
-    SmemLayout Lr = smem_layout(Tr, 0, 0, 0, MSLOTS, 8);
-    if ((e = cudaFuncSetAttribute(k_slots_rare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lr.total)) != cudaSuccess) return cudaGetErrorString(e);
-    unsigned long long rare_blocks = (n / 16 + 255) / 256;                       // sized for ~6 % rare frames; the kernel loops beyond that
-    if (rare_blocks < 1) rare_blocks = 1;
-    if (rare_blocks > (unsigned long long)sm_count() * 8) rare_blocks = (unsigned long long)sm_count() * 8;
-    k_slots_rare<<<(int)rare_blocks, 256, Lr.total, st>>>(Tr, (const uint8_t *)d_pkts, stride, rare_q, rare_cnt, flags, d_verdicts);
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -1145,7 +1148,7 @@ const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride
     const int minb = stages >> 4; stages &= 15;              // stages | minblocks << 4 (tuning knob CLK_STAGES / CLK_MINB)
     // every small table present is staged (and at least the endpoint table exists) -> shared-memory specialisation
     const bool all_staged = T.stage_ep_bytes && T.stage_soa_bytes && (!T.dns_b || T.stage_dns_bytes) && (!T.route_b || T.stage_route_bytes) &&
-                            (!T.n_cidr || T.stage_pre_bytes);
+                            (!T.n_cidr || T.stage_pre_bytes) && (!T.ep6 || T.stage_ep6_bytes);
     if (loader != LOADER_TMA_SW64) return launch_fast<2, false, 1, false>(FAST_ARGS);
     if (all_staged) {
         if (minb >= 2) return launch_fast<1, true, 2, true>(FAST_ARGS);                 // 2 x 1024 threads per SM (<= 32 registers)

@@ -114,7 +114,8 @@ struct DevTables {
     const EpRow    *ep_rows;     uint32_t n_ep_rows;
     const uint2    *ep_slots;    uint32_t ep_mask, ep_shift;   // slot: {ip, EpRow index + 1} (y == 0 empty), index hash_a(ip) >> ep_shift, load <= 1/4
     const uint4    *ep_rowq;                             // 3 x uint4 per EpRow index: {uid,mark,flags,crow} {envoy,coredns,gateway,hp_ip} {net,mask,hp_port|egress<<16,0}
-    const Ep6Key   *ep6;         uint32_t n_ep6;         // linear (<= 256 rows), rarely non-empty
+    const Ep6Key   *ep6;         uint32_t n_ep6, ep6_mask, ep6_shift;   // open addressing, 32 B slots {addr[4], row}; row == 0xffffffff empty;
+                                                                         // index hash_a(a0^a1^a2^a3) >> ep6_shift
     const ContRow  *crows;       uint32_t n_crows;
     const uint32_t *cg_slots;    uint32_t cg_mask;       // slot: ContRow index + 1, keyed by mix64(cgroup_id)
     const uint4    *dns_b;       uint32_t dns_shift;     // buckets; null => empty table; index hash_{a,b}(ip) >> dns_shift
@@ -134,7 +135,7 @@ struct DevTables {
     unsigned long long *m_dropped;                       // [0] increments dropped, [1] keys present
     uint32_t m_max;                                      // max_entries of metrics_map (common.h:173): inserts beyond it are dropped
     // sizes for optional shared-memory staging (bytes; 0 = do not stage)
-    uint32_t stage_ep_bytes, stage_soa_bytes, stage_dns_bytes, stage_route_bytes, stage_pre_bytes;
+    uint32_t stage_ep_bytes, stage_soa_bytes, stage_dns_bytes, stage_route_bytes, stage_pre_bytes, stage_ep6_bytes;
 };
 
 }  // namespace clk

@@ -199,7 +199,7 @@ int publish_locked(clk_engine *e)
         cg_slots[h] = (uint32_t)i + 1;
     }
     // ---- endpoint rows ----------------------------------------------------------------------------
-    std::vector<EpRow> rows; std::vector<Ep6Key> ep6;
+    std::vector<EpRow> rows; std::vector<Ep6Key> ep6_list, ep6;
     auto fill = [&](EpRow &r, const clk_endpoint &ep) {
         r.uid = ep.uid; r.cgroup_id = ep.cgroup_id; r.so_mark = ep.so_mark; r.crow = 0xffffffffu;
         auto it = e->crow_of.find(ep.cgroup_id);
@@ -216,9 +216,19 @@ int publish_locked(clk_engine *e)
     for (auto &kv : e->endpoint6) {
         EpRow r; memset(&r, 0, sizeof r); fill(r, kv.second);
         Ep6Key k; memset(&k, 0, sizeof k); memcpy(k.a, kv.first.data(), 16); k.row = (uint32_t)rows.size();
-        rows.push_back(r); ep6.push_back(k);
+        rows.push_back(r); ep6_list.push_back(k);
     }
     // ---- dns_cache / route_map --------------------------------------------------------------------
+    if (!ep6_list.empty()) {                                   // IPv6 endpoints: open addressing at load <= 1/4
+        Ep6Key empty; memset(&empty, 0, sizeof empty); empty.row = 0xffffffffu;
+        ep6.assign(pow2_at_least(ep6_list.size() * 4 + 1), empty);
+        const uint32_t mask = (uint32_t)ep6.size() - 1, sh = shift_for((uint32_t)ep6.size());
+        for (auto &k : ep6_list) {
+            uint32_t hh = hash_a(k.a[0] ^ k.a[1] ^ k.a[2] ^ k.a[3]) >> sh;
+            while (ep6[hh].row != 0xffffffffu) hh = (hh + 1) & mask;
+            ep6[hh] = k;
+        }
+    }
     // 2-choice bucketed tables (dev_tables.h): grow until every key fits one of its two buckets
     std::vector<uint4> dns_b, route_b;
     auto slot_empty = [](const uint4 &b, int k) { return k == 0 ? (b.x & b.y) == 0xffffffffu : (b.z & b.w) == 0xffffffffu; };
@@ -341,7 +351,8 @@ int publish_locked(clk_engine *e)
     T.ep_rows = rows.empty() ? nullptr : (const EpRow *)S.ep_rows.p; T.n_ep_rows = (uint32_t)rows.size();
     if (n_ep4) { T.ep_slots = (const uint2 *)S.ep_slots.p; T.ep_mask = (uint32_t)ep_slots.size() - 1; T.ep_shift = shift_for((uint32_t)ep_slots.size()); }
     T.ep_rowq = (const uint4 *)S.ep_soa.p;
-    T.ep6 = ep6.empty() ? nullptr : (const Ep6Key *)S.ep6.p; T.n_ep6 = (uint32_t)ep6.size();
+    T.ep6 = ep6.empty() ? nullptr : (const Ep6Key *)S.ep6.p; T.n_ep6 = (uint32_t)ep6_list.size();
+    if (!ep6.empty()) { T.ep6_mask = (uint32_t)ep6.size() - 1; T.ep6_shift = shift_for((uint32_t)ep6.size()); }
     T.crows = crows.empty() ? nullptr : (const ContRow *)S.crows.p; T.n_crows = (uint32_t)crows.size();
     T.cg_slots = (const uint32_t *)S.cg_slots.p; T.cg_mask = (uint32_t)cg_slots.size() - 1;
     if (!dns_b.empty()) { T.dns_b = (const uint4 *)S.dns.p; T.dns_shift = shift_for((uint32_t)dns_b.size()); }
@@ -366,6 +377,7 @@ int publish_locked(clk_engine *e)
         if (!dns_b.empty() && dns_b.size() * 16 <= 32768) T.stage_dns_bytes = (uint32_t)dns_b.size() * 16;
         if (!route_b.empty() && route_b.size() * 16 <= 8192) T.stage_route_bytes = (uint32_t)route_b.size() * 16;
         if (n_cidr) T.stage_pre_bytes = 8192;
+        if (!ep6.empty() && ep6.size() * 32 <= 8192) T.stage_ep6_bytes = (uint32_t)ep6.size() * 32;
     }
     e->T = T; e->active = 1 - e->active; e->published = true; e->dirty = false;
     return CLK_OK;
@@ -667,9 +679,9 @@ int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, u
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     LaunchInfo li = { 0, 0, 0 };
     cudaEventRecord(e->ev0, st);
-    CUDA_TRY(e, e->work_rare[3].ensure((n + 1) * 4));          // grows only when a larger batch arrives
+    CUDA_TRY(e, e->work_rare[3].ensure((n + 2) * 4));          // grows only when a larger batch arrives
     const char *err = launch_slots(e->T, d_pkts, stride, n, flags, (uint32_t *)d_verdicts, st, e->loader, e->stages,
-                                   (uint32_t *)e->work_rare[3].p + 1, (uint32_t *)e->work_rare[3].p, &li);
+                                   (uint32_t *)e->work_rare[3].p + 2, (uint32_t *)e->work_rare[3].p, &li);
     cudaEventRecord(e->ev1, st);
     return finish_launch(e, err, li);
 }
@@ -721,9 +733,9 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
         } else {
             CUDA_TRY(e, e->work_pkts[s].ensure(cnt * stride));
             CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + done * stride, cnt * stride, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(e, e->work_rare[s].ensure((cnt + 1) * 4));
+            CUDA_TRY(e, e->work_rare[s].ensure((cnt + 2) * 4));
             err = launch_slots(e->T, e->work_pkts[s].p, stride, cnt, flags, (uint32_t *)e->work_verd[s].p, st, e->loader, e->stages,
-                               (uint32_t *)e->work_rare[s].p + 1, (uint32_t *)e->work_rare[s].p, &li);
+                               (uint32_t *)e->work_rare[s].p + 2, (uint32_t *)e->work_rare[s].p, &li);
         }
         rc = finish_launch(e, err, li); if (rc) return rc;
         CUDA_TRY(e, cudaMemcpyAsync(verdicts + done, e->work_verd[s].p, cnt * 4, cudaMemcpyDeviceToHost, st));
