@@ -111,7 +111,7 @@ __device__ __noinline__ int dns_zone_select_exact(const DevTables &T, const uint
 // Converged form: a warp whose 32 lanes each hold a different DNS name advances label by label in lock step
 // through two forward passes (F = whole-name sum, then prefix sums), every lane stops at its FIRST hash
 // hit (the longest matching suffix), and the byte-for-byte confirmation runs once after the loop.
-__device__ __forceinline__ int dns_zone_select(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t off, uint32_t *after, uint32_t *zone_hash)
+__device__ __noinline__ int dns_zone_select(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t off, uint32_t *after, uint32_t *zone_hash)
 {
     // Common case first: an uncompressed name shorter than 64 octets (every real question name).  Hop over the
     // length octets once (remembering where they are in a 64-bit mask), then ONE right-to-left Horner pass
@@ -224,7 +224,7 @@ __device__ __forceinline__ int dns_skip_name(const uint8_t *m, uint32_t mlen, ui
 }
 
 // dnsbpf.Handler.writeARecords over the wire form.  out == nullptr: count only.
-__device__ __forceinline__ uint32_t dns_answer_updates(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t pkt_index,
+__device__ __noinline__ uint32_t dns_answer_updates(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t pkt_index,
                                                        clk_dns_update_rec *out, unsigned long long pos, unsigned long long cap, uint32_t *name_v)
 {
     *name_v = CLK_N_DENY;
@@ -332,7 +332,7 @@ __device__ __forceinline__ bool sni_match(const DevTables &T, const uint8_t *hos
     return sni_match_exact(T, host, n);
 }
 
-__device__ __forceinline__ uint32_t tls_sni_verdict(const DevTables &T, const uint8_t *p, uint32_t n)
+__device__ __noinline__ uint32_t tls_sni_verdict(const DevTables &T, const uint8_t *p, uint32_t n)
 {
     if (n < 9 || gb(p) != 0x16u || gb(p + 1) != 0x03u) return CLK_N_DENY;
     uint32_t rlen = gbe16(p + 3);

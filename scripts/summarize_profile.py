@@ -1,8 +1,9 @@
 """Turn gpurun_out/<name>.ncu-rep (+ launch list csv) into committed evidence under profiles/.
-usage: summarize_profile.py <round tag e.g. r01> <ncu-rep> <kernel substring> <packets per launch> [launch csv]"""
+usage: summarize_profile.py <tag e.g. r01 or r01_varlen> <ncu-rep> <kernel substring> <packets per launch> [launch csv] [algorithmic bytes per packet]"""
 import csv, json, subprocess, sys, os, collections, io
 tag, rep, kern, npk = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4])
-launch_csv = sys.argv[5] if len(sys.argv) > 5 else None
+launch_csv = sys.argv[5] if len(sys.argv) > 5 and sys.argv[5] != '-' else None
+bpp = float(sys.argv[6]) if len(sys.argv) > 6 else 68.0
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(root, "profiles"); os.makedirs(out_dir, exist_ok=True)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -41,8 +42,8 @@ for w in want:
     v, u = g(w)
     if v is not None: lines.append(f"| {w} | {v} | {u} |")
 lines += ["", f"- DRAM traffic per launch: {traffic/1e6:.1f} MB (read {to_bytes(*rd)/1e6:.1f} + write {to_bytes(*wr)/1e6:.1f}); "
-          f"algorithmic bytes {npk*68/1e6:.1f} MB (68 B/packet) -> traffic/algorithmic = {traffic/(npk*68):.3f}",
-          f"- duration under ncu {dur_us:.1f} us -> {npk*68/dur_us/1e3:.0f} GB/s algorithmic (cold cache; the bench's CUDA-event number is the one to quote)",
+          f"algorithmic bytes {npk*bpp/1e6:.1f} MB ({bpp:g} B/packet) -> traffic/algorithmic = {traffic/(npk*bpp):.3f}",
+          f"- duration under ncu {dur_us:.1f} us -> {npk*bpp/dur_us/1e3:.0f} GB/s algorithmic (cold cache; the bench's CUDA-event number is the one to quote)",
           f"- warp-instructions per 32-packet tile: {n_inst/(npk/32):.0f}", "", "Warp stall samples:", ""]
 for k, v in st.most_common(10): lines.append(f"- {k}: {100*v/tot:.1f}%")
 if launch_csv:
@@ -61,6 +62,6 @@ if launch_csv:
     import shutil; shutil.copy(launch_csv, os.path.join(out_dir, f"{tag}_launches.csv"))
 open(os.path.join(out_dir, f"{tag}_summary.md"), "w").write("\n".join(lines) + "\n")
 json.dump({"kernel": kern, "packets_per_launch": npk, "dram_bytes_per_launch": traffic, "dram_read": to_bytes(*rd), "dram_write": to_bytes(*wr),
-           "algorithmic_bytes_per_launch": npk * 68, "ncu_duration_us": dur_us, "source": os.path.basename(rep)},
+           "algorithmic_bytes_per_launch": npk * bpp, "ncu_duration_us": dur_us, "source": os.path.basename(rep)},
           open(os.path.join(out_dir, f"{tag}_traffic.json"), "w"), indent=1)
 print("\n".join(lines))
