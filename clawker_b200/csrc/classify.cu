@@ -1027,17 +1027,27 @@ __global__ void __launch_bounds__(256) k_positions(const uint32_t *__restrict__ 
 // ------------------------------------------------------------------------------------------------
 // counters block export / import (the payload of the one multi-GPU collective)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_counters_export(const __grid_constant__ DevTables T, clk_metric *__restrict__ block)
+// Compacted export: block[0] is a header whose `count` is the number of rows that follow; rows 1..count are
+// the occupied metrics_map entries in no particular order (cap_rows bounds the block).
+__global__ void k_counters_export(const __grid_constant__ DevTables T, clk_metric *__restrict__ block, uint32_t cap_rows)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.m_mask; i += gridDim.x * blockDim.x) {
-        unsigned long long k = T.m_keys[i]; clk_metric m;
-        m.key.cgroup_id = 0; m.key.domain_hash = 0; m.key.dst_port = 0; m.key.action = 0; m.key._pad = 0; m.count = 0;
+    const uint32_t lane = threadIdx.x & 31u, slots = T.m_mask + 1, slots_round = (slots + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < slots_round; i += gridDim.x * blockDim.x) {
+        const unsigned long long k = i < slots ? T.m_keys[i] : 0ull;
+        const unsigned m = __ballot_sync(0xffffffffu, k != 0ull);
+        if (!m) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd((unsigned long long *)&block[0].count, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
         if (k) {
-            uint32_t crow = (uint32_t)(k >> 48) & 0x3fffu;
-            m.key.cgroup_id = T.crows[crow].cgroup_id; m.key.domain_hash = (uint32_t)k; m.key.dst_port = (uint16_t)(k >> 32);
-            m.key.action = (uint8_t)((k >> 62) - 1); m.count = T.m_counts[i];
+            const unsigned long long pos = 1 + base + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap_rows) {
+                clk_metric r; const uint32_t crow = (uint32_t)(k >> 48) & 0x3fffu;
+                r.key.cgroup_id = T.crows[crow].cgroup_id; r.key.domain_hash = (uint32_t)k; r.key.dst_port = (uint16_t)(k >> 32);
+                r.key.action = (uint8_t)((k >> 62) - 1); r.key._pad = 0; r.count = T.m_counts[i];
+                block[pos] = r;
+            }
         }
-        block[i] = m;
     }
 }
 __global__ void k_counters_clear(const __grid_constant__ DevTables T)
@@ -1045,9 +1055,15 @@ __global__ void k_counters_clear(const __grid_constant__ DevTables T)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.m_mask; i += gridDim.x * blockDim.x) { T.m_keys[i] = 0ull; T.m_counts[i] = 0ull; }
     if (blockIdx.x == 0 && threadIdx.x == 0) { T.m_dropped[0] = 0ull; T.m_dropped[1] = 0ull; }
 }
-__global__ void k_counters_import(const __grid_constant__ DevTables T, const clk_metric *__restrict__ blocks, unsigned long long rows)
+__global__ void k_counters_import(const __grid_constant__ DevTables T, const clk_metric *__restrict__ blocks, uint32_t n_blocks, uint32_t block_rows)
 {
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long total = (unsigned long long)n_blocks * block_rows;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t)(i / block_rows), r = (uint32_t)(i % block_rows);
+        if (r == 0) continue;                                               // header
+        unsigned long long valid = blocks[(unsigned long long)b * block_rows].count;
+        if (valid > block_rows - 1) valid = block_rows - 1;
+        if (r > valid) continue;
         clk_metric m = blocks[i];
         if (m.count == 0) continue;
         uint32_t h = mix64(m.key.cgroup_id) & T.cg_mask, crow = 0xffffffffu;
@@ -1211,19 +1227,24 @@ const char *launch_dns_extract(const DevTables &T, const void *d_pkts, const uin
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
-const char *launch_counters_export(const DevTables &T, clk_metric *d_block, cudaStream_t st)
+const char *launch_counters_export(const DevTables &T, clk_metric *d_block, uint32_t cap_rows, cudaStream_t st)
 {
-    k_counters_export<<<sm_count() * 2, 256, 0, st>>>(T, d_block);
-    cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+    cudaError_t e = cudaMemsetAsync(d_block, 0, sizeof(clk_metric), st);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    k_counters_export<<<sm_count() * 8, 256, 0, st>>>(T, d_block, cap_rows);
+    e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 const char *launch_counters_clear(const DevTables &T, cudaStream_t st)
 {
-    k_counters_clear<<<sm_count() * 2, 256, 0, st>>>(T);
+    k_counters_clear<<<sm_count() * 8, 256, 0, st>>>(T);
     cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
-const char *launch_counters_import(const DevTables &T, const clk_metric *d_blocks, unsigned long long rows, cudaStream_t st)
+const char *launch_counters_import(const DevTables &T, const clk_metric *d_blocks, uint32_t n_blocks, uint32_t block_rows, cudaStream_t st)
 {
-    k_counters_import<<<sm_count() * 2, 256, 0, st>>>(T, d_blocks, rows);
+    unsigned long long blocks = ((unsigned long long)n_blocks * block_rows + 255) / 256;   // one row per thread: the adds are L2-latency bound
+    if (blocks > (unsigned long long)sm_count() * 64) blocks = (unsigned long long)sm_count() * 64;
+    if (blocks < 1) blocks = 1;
+    k_counters_import<<<(int)blocks, 256, 0, st>>>(T, d_blocks, n_blocks, block_rows);
     cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

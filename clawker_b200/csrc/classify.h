@@ -20,8 +20,8 @@ const char *launch_events(const DevTables &T, const clk_event *d_ev, unsigned lo
 const char *launch_dns_extract(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n,
                                const uint32_t *d_verdicts, unsigned long long *d_block_sums, unsigned long long *d_pos,
                                unsigned long long *d_total, clk_dns_update_rec *d_out, unsigned long long cap, cudaStream_t st);
-const char *launch_counters_export(const DevTables &T, clk_metric *d_block, cudaStream_t st);
+const char *launch_counters_export(const DevTables &T, clk_metric *d_block, uint32_t cap_rows, cudaStream_t st);
 const char *launch_counters_clear(const DevTables &T, cudaStream_t st);
-const char *launch_counters_import(const DevTables &T, const clk_metric *d_blocks, unsigned long long rows, cudaStream_t st);
+const char *launch_counters_import(const DevTables &T, const clk_metric *d_blocks, uint32_t n_blocks, uint32_t block_rows, cudaStream_t st);
 
 }  // namespace clk

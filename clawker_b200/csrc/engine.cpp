@@ -822,7 +822,7 @@ int clk_dns_answers(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, 
 int clk_counters_block_rows(clk_engine *e, uint32_t *rows)
 {
     if (!e || !rows) return fail(e, CLK_EINVAL, "NULL");
-    *rows = e->T.m_mask + 1;
+    *rows = e->max_metrics + 1 + 1024;     // header + max_entries (+ slack: the entry cap is enforced without a lock)
     return CLK_OK;
 }
 
@@ -832,7 +832,7 @@ int clk_counters_export(clk_engine *e, void *d_block, void *stream)
     NEED_GPU(e);
     std::lock_guard<std::mutex> g(e->mu);
     int rc = ensure_published(e); if (rc) return rc;
-    const char *err = launch_counters_export(e->T, (clk_metric *)d_block, stream ? (cudaStream_t)stream : e->stream);
+    const char *err = launch_counters_export(e->T, (clk_metric *)d_block, e->max_metrics + 1 + 1024, stream ? (cudaStream_t)stream : e->stream);
     if (err) return fail(e, CLK_EIO, "counters export: %s", err);
     e->stats.kernel_launches++;
     return CLK_OK;
@@ -856,7 +856,7 @@ int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, 
     CUDA_TRY(e, e->g_keys.ensure(slots * 8)); CUDA_TRY(e, e->g_counts.ensure(slots * 8)); CUDA_TRY(e, e->g_dropped.ensure(16));
     DevTables G = global_view(e);
     const char *err = launch_counters_clear(G, st);
-    if (!err) err = launch_counters_import(G, (const clk_metric *)d_blocks, (unsigned long long)n_blocks * slots, st);
+    if (!err) err = launch_counters_import(G, (const clk_metric *)d_blocks, n_blocks, e->max_metrics + 1 + 1024, st);
     if (err) return fail(e, CLK_EIO, "counters import: %s", err);
     e->stats.kernel_launches += 2;
     return CLK_OK;
@@ -871,18 +871,18 @@ static int counters_read_impl(clk_engine *e, bool global, clk_metric *out, uint3
     if (global && !e->g_keys.p) { *n = 0; return CLK_OK; }
     CUDA_TRY(e, cudaSetDevice(e->device));
     CUDA_TRY(e, cudaDeviceSynchronize());
-    uint32_t rows = e->T.m_mask + 1;
+    uint32_t rows = e->T.m_mask + 2;                            // header + every slot (the merged view may hold more than max_entries)
     CUDA_TRY(e, e->ctr_block.ensure((size_t)rows * sizeof(clk_metric)));
     DevTables V = global ? global_view(e) : e->T;
-    const char *err = launch_counters_export(V, (clk_metric *)e->ctr_block.p, e->stream);
+    const char *err = launch_counters_export(V, (clk_metric *)e->ctr_block.p, rows, e->stream);
     if (err) return fail(e, CLK_EIO, "counters export: %s", err);
     e->stats.kernel_launches++;
     std::vector<clk_metric> host(rows);
     CUDA_TRY(e, cudaMemcpyAsync(host.data(), e->ctr_block.p, (size_t)rows * sizeof(clk_metric), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(&e->stats.metrics_dropped, V.m_dropped, 8, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    uint32_t k = 0;
-    for (auto &m : host) if (m.count) { if (out && k < cap) out[k] = m; k++; }
+    uint32_t k = 0; const uint64_t valid = std::min<uint64_t>(host[0].count, rows - 1);
+    for (uint64_t i = 1; i <= valid; i++) if (host[i].count) { if (out && k < cap) out[k] = host[i]; k++; }
     *n = k;
     return CLK_OK;
 }
