@@ -545,7 +545,7 @@ __host__ __device__ inline SmemLayout smem_layout(const DevTables &T, uint32_t t
     L.pre = o; o += (T.stage_pre_bytes + 15u) & ~15u;
     L.ep6 = o; o += (T.stage_ep6_bytes + 15u) & ~15u;
     L.queue = o; o += queue_bytes;
-    L.bars = o; o += (n_bars + 1) * 8;
+    L.bars = o; o += (n_bars + 1) * 8 + 16;                // + a CTA-wide counter word after the barriers
     L.total = o;
     return L;
 }
@@ -566,7 +566,7 @@ __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, 
     tb.ep = T.ep_slots; tb.ep_mask = T.ep_mask; tb.ep_shift = T.ep_shift; tb.rowq = T.ep_rowq;
     tb.dns = T.dns_b; tb.dns_shift = T.dns_shift; tb.route = T.route_b; tb.route_shift = T.route_shift; tb.pre = T.cidr_pre; tb.ep6 = T.ep6;
     const uint32_t nb = T.stage_ep_bytes + T.stage_soa_bytes + T.stage_dns_bytes + T.stage_route_bytes + T.stage_pre_bytes + T.stage_ep6_bytes;
-    if (threadIdx.x == 0) { for (uint32_t i = 0; i <= n_bars; i++) mbar_init(&bars[i], 1); fence_mbar_init(); }
+    if (threadIdx.x == 0) { for (uint32_t i = 0; i <= n_bars; i++) mbar_init(&bars[i], 1); *(uint32_t *)&bars[n_bars + 1] = 0; fence_mbar_init(); }
     __syncthreads();
     if (nb) {
         if (threadIdx.x == 0) {
@@ -719,6 +719,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
             if (t < n_tiles) { mbar_expect_tx(&bars[s], WTILE_BYTES); tma_load_2d(tiles + s * WTILE_BYTES, &map, &bars[s], 0, (int)(t << 5)); }
         }
     }
+    // rare frames: per-warp staging queue -> this CTA's own region of rare_q (no cross-CTA traffic, no grid barrier)
+    const uint32_t cta_cap = ((n_tiles + W - 1) / W) * FAST_WARPS * 32;
+    uint32_t *cta_q = rare_q + (size_t)blockIdx.x * cta_cap;
+    uint32_t *cta_cnt = (uint32_t *)(smem + L.bars) + 2 * (FAST_WARPS * kStages + 1);   // one word after the mbarriers
     uint32_t qn = 0;                                         // entries in this warp's queue (warp-uniform)
     uint32_t it = 0;
     for (uint32_t t = gw; t < n_tiles; t += W, it++) {
@@ -749,9 +753,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
         if (do_metrics) metric_warp_emit(T, ag, hm, mk);
         if (qn >= 32) {                                                      // hand 32 rare packets to k_slots_rare
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(rare_cnt, 32u);
+            if (lane == 0) base = atomicAdd(cta_cnt, 32u);
             base = __shfl_sync(0xffffffffu, base, 0);
-            rare_q[base + lane] = queue[lane];
+            cta_q[base + lane] = queue[lane];
             const uint32_t carry = lane + 32 < qn ? queue[lane + 32] : 0;
             __syncwarp();
             if (lane + 32 < qn) queue[lane] = carry;
@@ -761,28 +765,21 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
     }
     if (qn) {                                                                // leftovers (< 32)
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(rare_cnt, qn);
+        if (lane == 0) base = atomicAdd(cta_cnt, qn);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < qn) rare_q[base + lane] = queue[lane];
+        if (lane < qn) cta_q[base + lane] = queue[lane];
     }
     // ---- rare frames (IPv6, IPv4 options, malformed; a few % of a realistic mix) ------------------------------
-    // Every CTA of this launch is resident (grid = SMs x occupancy), so a counter barrier across the grid is safe.
-    // After it the whole grid walks the compacted queue with the generic path, all lanes busy, tables and the
-    // metric cache still in shared memory — no second launch, no second prologue / flush.
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        atomicAdd(&rare_cnt[1], 1u);
-        while (*(volatile uint32_t *)&rare_cnt[1] < gridDim.x) { }
-        __threadfence();
-    }
+    // Each CTA classifies the rare frames of its own tiles once its main loop is done: the generic path with every
+    // lane busy, tables and the metric cache still in shared memory.
+    __threadfence_block();
     __syncthreads();
     {
-        const uint32_t cnt = *(volatile uint32_t *)&rare_cnt[0], cnt_round = (cnt + 31u) & ~31u;
-        for (uint32_t k = (gw << 5) + lane; k < cnt_round; k += W << 5) {
+        const uint32_t cnt = *(volatile uint32_t *)cta_cnt, cnt_round = (cnt + 31u) & ~31u;
+        for (uint32_t k = tid; k < cnt_round; k += FAST_WARPS * 32) {
             bool hm = false; unsigned long long mk = 0;
             if (k < cnt) {
-                const unsigned long long j = rare_q[k];
+                const unsigned long long j = cta_q[k];
                 stg_stream(&verdicts[j], generic_one(T, tb, pkts + j * stride, stride, flags & ~CLK_F_NAME_STAGE, hm, mk));
             }
             if (do_metrics) metric_warp_emit(T, ag, hm, mk);
@@ -1127,7 +1124,6 @@ static const char *launch_fast(const DevTables &T, const CUtensorMap &map, const
     if ((e = occupancy_grid(k_slots_fast<kStages, kSwizzle, kMinBlocks, kAllStaged>, FAST_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long n_cta = ((n + 31) / 32 + FAST_WARPS - 1) / FAST_WARPS;
     if ((unsigned long long)grid > n_cta) grid = (int)n_cta;
-    if ((e = cudaMemsetAsync(rare_cnt, 0, 8, st)) != cudaSuccess) return cudaGetErrorString(e);     // [0] queue length, [1] grid barrier
     k_slots_fast<kStages, kSwizzle, kMinBlocks, kAllStaged><<<grid, FAST_WARPS * 32, L.total, st>>>(T, map, (const uint8_t *)d_pkts, stride, rare_q, rare_cnt, agg_slots, n, flags, d_verdicts);
     if (info) { info->grid = grid; info->block = FAST_WARPS * 32; info->smem = L.total; }
     e = cudaGetLastError();

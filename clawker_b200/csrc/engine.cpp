@@ -679,7 +679,7 @@ int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, u
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     LaunchInfo li = { 0, 0, 0 };
     cudaEventRecord(e->ev0, st);
-    CUDA_TRY(e, e->work_rare[3].ensure((n + 2) * 4));          // grows only when a larger batch arrives
+    CUDA_TRY(e, e->work_rare[3].ensure((n + (1u << 20)) * 4)); // per-CTA regions (packets of the CTA's tiles); grows only for larger batches
     const char *err = launch_slots(e->T, d_pkts, stride, n, flags, (uint32_t *)d_verdicts, st, e->loader, e->stages,
                                    (uint32_t *)e->work_rare[3].p + 2, (uint32_t *)e->work_rare[3].p, &li);
     cudaEventRecord(e->ev1, st);
@@ -733,7 +733,7 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
         } else {
             CUDA_TRY(e, e->work_pkts[s].ensure(cnt * stride));
             CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + done * stride, cnt * stride, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(e, e->work_rare[s].ensure((cnt + 2) * 4));
+            CUDA_TRY(e, e->work_rare[s].ensure((cnt + (1u << 20)) * 4));
             err = launch_slots(e->T, e->work_pkts[s].p, stride, cnt, flags, (uint32_t *)e->work_verd[s].p, st, e->loader, e->stages,
                                (uint32_t *)e->work_rare[s].p + 2, (uint32_t *)e->work_rare[s].p, &li);
         }
