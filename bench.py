@@ -33,8 +33,12 @@ import numpy as np
 
 METRIC = "Mpackets/sec egress-verdict throughput"
 WORKLOADS = {
-    "c2": dict(n=10_000_000, gen=2_000_000, layout="slots", cfg="c2",
-               desc="10M-packet synthetic pcap (64 B slots), 1k IP/CIDR rules, 8 containers"),
+    # IPv4, 85 % TCP / 14 % UDP / 1 % other, dst 50 % from the rule set, dport Zipf incl. random, 3 % unmanaged sources
+    "c2": dict(n=10_000_000, gen=2_000_000, layout="slots", cfg="c2", mix=dict(v6_frac=0.0, nonip_frac=0.0),
+               desc="10M-packet synthetic pcap (64 B slots, IPv4 85/14/1 % TCP/UDP/other), 1k IP/CIDR rules, 8 containers"),
+    # the same with 2 % IPv6 and 0.5 % non-IP frames mixed in (the parity-test mix)
+    "c2v6": dict(n=10_000_000, gen=2_000_000, layout="slots", cfg="c2", mix=dict(v6_frac=0.02, nonip_frac=0.005),
+                 desc="10M-packet synthetic pcap (64 B slots) incl. 2 % IPv6 + 0.5 % non-IP, 1k IP/CIDR rules, 8 containers"),
     "c3": dict(n=100_000_000, gen=1_000_000, layout="varlen", cfg="c3",
                desc="100M packets incl. DNS + TLS-SNI (70/10/5/15 % header-only/DNS query/DNS answer/ClientHello), 10k-domain allowlist, name stage on"),
     "c5": dict(n=100_000_000, gen=2_000_000, layout="slots", cfg="c5:1000", desc="64 B min-size packet flood, 100M packets/GPU"),
@@ -88,7 +92,7 @@ def make_batch(workload: str, rank: int):
     spec = WORKLOADS[workload]
     w = capture.make_workload(spec["cfg"])
     if spec["layout"] == "slots":
-        return w, (capture.gen_slots(w, spec["gen"], seed=2 + 1000 * rank), None), spec
+        return w, (capture.gen_slots(w, spec["gen"], seed=2 + 1000 * rank, **spec.get("mix", {})), None), spec
     blob, offs, _ = capture.gen_varlen(w, spec["gen"], seed=3 + 1000 * rank, pool=8192)
     return w, (blob, offs), spec
 

@@ -72,3 +72,51 @@ def test_gpu_matches_oracle_on_name_cases():
     assert e.map_lookup(abi.MAP_DNS_CACHE, C.c_uint32(capture.ip4("140.82.121.4")), v) is not None
     # last write in packet order wins (UpdateAny): the later "0.0.0.0 is skipped" answer re-resolves it with TTL 60
     assert v.domain_hash == rules_oracle.domain_hash("github.com") and v.expire_ts == 1060
+
+
+def _mutated_batch(seed: int, n: int = 6000):
+    """Name-stage frames with random byte / length corruption (parsers must agree on every malformed input)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = [fr for _, fr, _, _ in NC.CASES]
+    frames = []
+    for _ in range(n):
+        fr = bytearray(base[int(rng.integers(0, len(base)))])
+        k = int(rng.integers(0, 4))
+        for _m in range(k):
+            op = int(rng.integers(0, 4))
+            lo = 34 if len(fr) > 60 else 12                   # mostly hit L4 header + payload, sometimes L3
+            pos = int(rng.integers(lo, len(fr)))
+            if op == 0:
+                fr[pos] = int(rng.integers(0, 256))
+            elif op == 1:
+                fr[pos] ^= 1 << int(rng.integers(0, 8))
+            elif op == 2 and len(fr) > 60:
+                del fr[int(rng.integers(54, len(fr))):]      # truncate the payload (IP total length now lies)
+            else:
+                fr[pos:pos] = bytes(int(x) for x in rng.integers(0, 256, size=int(rng.integers(1, 9))))
+        frames.append(bytes(fr))
+    return capture.build_varlen(frames)
+
+
+def test_oracle_survives_mutations():
+    blob, offs = _mutated_batch(1, 3000)
+    v, _ = oracle.Oracle("port").load(_tables()).classify(blob, offs, flags=abi.F_NAME_STAGE)
+    assert v.size == offs.size - 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_gpu_matches_oracle_on_mutated_frames(seed):
+    from util import assert_same_verdicts
+    from clawker_b200 import engine
+    blob, offs = _mutated_batch(seed)
+    o = oracle.Oracle("port").load(_tables())
+    want, wm = o.classify(blob, offs, flags=abi.F_NAME_STAGE)
+    e = engine.Engine(max_metrics=1 << 16)
+    e.load_tables(capture.base_tables(8))
+    e.compile_rules(NC.RULES)
+    e.publish()
+    got = e.classify_varlen(blob, offs, flags=abi.F_NAME_STAGE)
+    assert_same_verdicts(got, want, f"mutated frames seed {seed}")
+    a, b = e.dns_answers(blob, offs, got), o.dns_answers(blob, offs)
+    assert a.size == b.size and np.array_equal(a, b)
