@@ -203,13 +203,18 @@ def run_gpu(args) -> None:
 
     # metrics_map max_entries: 8x the reference default (common.h:173) so every key of the synthetic capture is counted;
     # keys beyond max_entries are dropped like the reference BPF_NOEXIST insert into a full map (--metrics-capacity)
-    e = engine.Engine(device=local, max_metrics=args.metrics_capacity, max_dns_cache=1 << 21, max_routes=1 << 16)
+    # multi-GPU: the classify kernels leave a few SMs to the side stream so the per-batch collective never delays them
+    reserved = args.reserved_sms if args.reserved_sms >= 0 else (4 if world > 1 else 0)
+    e = engine.Engine(device=local, max_metrics=args.metrics_capacity, max_dns_cache=1 << 21, max_routes=1 << 16, reserved_sms=reserved)
     e.load_tables(w.tables)
     e.compile_rules(w.rules)
     e.publish()
     rows = e.counters_block_rows()
     d_block = torch.empty(rows * 24, dtype=torch.uint8, device=dev)
     d_gather = torch.empty(world * rows * 24, dtype=torch.uint8, device=dev) if world > 1 else None
+    trow = e.totals_rows()
+    d_tot = torch.zeros(trow * 32, dtype=torch.uint8, device=dev)
+    d_tot_all = torch.zeros(world * trow * 32, dtype=torch.uint8, device=dev) if world > 1 else None
 
     ts = torch.cuda.Stream(device=dev)
     side = torch.cuda.Stream(device=dev)                           # the collective overlaps the next batch's kernel
@@ -225,15 +230,23 @@ def run_gpu(args) -> None:
             e.classify_slots_dev(d_pk.data_ptr(), 64, n, flags, d_v.data_ptr(), st)
         if ev_pair:
             ev_pair[1].record(ts)
-        if world > 1:                                              # the one collective: per-GPU counters over NVLink
+        if world > 1:                                              # per batch: per-container totals of every GPU over NVLink
             side.wait_stream(ts)
             with torch.cuda.stream(side):
-                e.counters_export(d_block.data_ptr(), side.cuda_stream)
-                dist.all_gather_into_tensor(d_gather, d_block)
-                e.counters_import(d_gather.data_ptr(), world, side.cuda_stream)
+                e.totals_export(d_tot.data_ptr(), side.cuda_stream)
+                dist.all_gather_into_tensor(d_tot_all, d_tot)
+
+    def merge_on_read():                                           # per-key merge of the metrics_map tables: once per read
+        with torch.cuda.stream(side):
+            e.counters_export(d_block.data_ptr(), side.cuda_stream)
+            dist.all_gather_into_tensor(d_gather, d_block)
+            e.counters_import(d_gather.data_ptr(), world, side.cuda_stream)
 
     for _ in range(max(3, args.warmup)):
         step()
+    if world > 1:
+        side.wait_stream(ts)
+        merge_on_read()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -254,6 +267,18 @@ def run_gpu(args) -> None:
         dist.barrier()
     ms_total = t0.elapsed_time(t1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_events]))
+    merge_ms = None
+    if world > 1:                                                  # what one reader of the merged metrics_map costs (not a per-batch step)
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(side)
+        merge_on_read()
+        m1.record(side)
+        torch.cuda.synchronize()
+        merge_ms = m0.elapsed_time(m1)
+        tot = e.totals_merge(d_tot_all.data_ptr(), world)
+        mg = e.counters(merged=True)
+        for a in range(3):                                         # the two forms of the sum must agree
+            assert int(tot["count"][:, a].sum()) == int(mg["count"][mg["action"] == a].sum()), "per-container totals != merged metrics_map"
     launches = e.stats().kernel_launches - launches0
 
     # ---- end to end: host buffers through the C-ABI (H2D + kernel + D2H inside the timed region) ----
@@ -305,7 +330,9 @@ def run_gpu(args) -> None:
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": spec["desc"], "packets_per_gpu_per_step": n, "rules": len(w.rules), "layout": "varlen (16 B aligned frames + u32 offsets)" if varlen else "64 B slots",
                        "l2_policy": f"inputs_larger_than_l2 ({n * bytes_per_packet / 1e6:.0f} MB per step vs 126 MB L2)",
-                       "parallelism": f"packet shards x{world}, tables replicated, 1 NCCL all-gather of counters per step" if world > 1 else "single GPU"},
+                       "parallelism": (f"packet shards x{world}, tables replicated, no data-path collective; per step 1 NCCL all-gather of per-container totals "
+                                       f"({trow * 32} B per GPU, side stream, {reserved} SMs reserved); per-key metrics_map merge on read, outside the timed region "
+                                       f"({merge_ms:.3f} ms per read)") if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": how, "kernel": "clk::k_varlen_fast" if varlen else "clk::k_slots_fast", "kernel_ms": round(kern_ms, 4),
                          "algorithmic_bytes_per_packet": round(bytes_per_packet, 2)},
@@ -331,6 +358,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--packets", type=int, default=0, help="override packets per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reserved-sms", type=int, default=-1, help="SMs the classify kernels leave to the side-stream collective (default: 4 when N > 1, else 0)")
     ap.add_argument("--metrics-capacity", type=int, default=131072, help="metrics_map max_entries per GPU (reference: 16384; the synthetic capture produces ~76k distinct keys)")
     args = ap.parse_args()
     if args.impl == "reference":

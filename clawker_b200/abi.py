@@ -44,7 +44,7 @@ class Cidr(C.Structure):
 class Cfg(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("max_containers", C.c_uint32),
                 ("max_dns_cache", C.c_uint32), ("max_routes", C.c_uint32), ("max_metrics", C.c_uint32),
-                ("max_cidrs", C.c_uint32), ("flags", C.c_uint32)]
+                ("max_cidrs", C.c_uint32), ("flags", C.c_uint32), ("reserved_sms", C.c_uint32)]
 
 
 class Rule(C.Structure):
@@ -65,8 +65,9 @@ EVENT_DTYPE = np.dtype([("cgroup_id", "<u8"), ("uid", "<u4"), ("so_mark", "<u4")
                         ("user_ip6", "<u4", (4,)), ("user_port", "<u2"), ("hook", "u1"), ("sock_type", "u1")])
 METRIC_DTYPE = np.dtype([("cgroup_id", "<u8"), ("domain_hash", "<u4"), ("dst_port", "<u2"), ("action", "u1"),
                          ("_pad", "u1"), ("count", "<u8")])
+TOTAL_DTYPE = np.dtype([("cgroup_id", "<u8"), ("count", "<u8", (3,))])           # clk_total: ALLOW, DENY, BYPASS
 DNSUPD_DTYPE = np.dtype([("ip", "<u4"), ("domain_hash", "<u4"), ("ttl", "<u4"), ("packet", "<u4")])
-assert EVENT_DTYPE.itemsize == 40 and METRIC_DTYPE.itemsize == 24 and DNSUPD_DTYPE.itemsize == 16
+assert EVENT_DTYPE.itemsize == 40 and METRIC_DTYPE.itemsize == 24 and DNSUPD_DTYPE.itemsize == 16 and TOTAL_DTYPE.itemsize == 32
 
 MAP_CONTAINER, MAP_BYPASS, MAP_DNS_CACHE, MAP_ROUTE, MAP_METRICS, MAP_ENDPOINT, MAP_ENDPOINT6, MAP_CIDR = range(8)
 F_NAME_STAGE, F_NO_METRICS = 1, 2

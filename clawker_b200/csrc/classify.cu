@@ -301,22 +301,31 @@ __device__ __forceinline__ uint32_t mhash(unsigned long long key)
 // path stays two instructions long).  Returns the increments it had to drop.
 __device__ __noinline__ unsigned int metric_global_slow(const DevTables &T, unsigned long long key, unsigned int cnt, uint32_t h)
 {
+    // A new key is a BPF_NOEXIST insert, refused once the map holds max_entries (metric_inc common.h:206-209).  The
+    // bound is strict, as in the kernel's hash map: an insert first takes a ticket from the key counter and gives it
+    // back if it loses the slot to the same key or finds the map full.  The merged view (import) is uncapped.
+    const bool capped = T.m_max != 0xffffffffu;
+    bool ticket = false; unsigned int lost = cnt;
     #pragma unroll 1
     for (int p = 0; p < 64; p++) {
         unsigned long long cur = T.m_keys[h];
         if (cur != key) {
             if (cur != 0ull) { h = (h + 1) & T.m_mask; continue; }
-            // a new key: BPF_NOEXIST insert, refused once the map holds max_entries (metric_inc common.h:206-209)
-            const bool capped = T.m_max != 0xffffffffu;                 // the merged view (import) is uncapped and uncounted
-            if (capped && *(volatile unsigned long long *)&T.m_dropped[1] >= T.m_max) break;
+            if (capped && !ticket) {
+                if (*(volatile unsigned long long *)&T.m_dropped[1] >= T.m_max) break;
+                if (atomicAdd(&T.m_dropped[1], 1ull) >= T.m_max) { atomicAdd(&T.m_dropped[1], ~0ull); break; }
+                ticket = true;
+            }
             cur = atomicCAS(&T.m_keys[h], 0ull, key);
-            if (cur == 0ull) { if (capped) atomicAdd(&T.m_dropped[1], 1ull); }
+            if (cur == 0ull) ticket = false;                            // inserted: the ticket is spent
             else if (cur != key) { h = (h + 1) & T.m_mask; continue; }
         }
         atomicAdd(&T.m_counts[h], (unsigned long long)cnt);
-        return 0u;
+        lost = 0u;
+        break;
     }
-    return cnt;
+    if (ticket) atomicAdd(&T.m_dropped[1], ~0ull);
+    return lost;
 }
 
 __device__ __forceinline__ unsigned int metric_global_add(const DevTables &T, unsigned long long key, unsigned int cnt)
@@ -1047,6 +1056,37 @@ __global__ void k_counters_export(const __grid_constant__ DevTables T, clk_metri
         }
     }
 }
+// Dense per-container totals of the local metrics_map: block[r] = {cgroup_id of container row r, ALLOW, DENY, BYPASS}.
+// This is the small per-batch collective payload (rows x 32 B); the caller zeroes `block` first.  A warp groups its 32
+// slots by (container row, action) and sums each group with three REDUX adds over 22-bit pieces of the counts.
+__global__ void k_counters_totals(const __grid_constant__ DevTables T, clk_total *__restrict__ block, uint32_t rows)
+{
+    extern __shared__ unsigned long long tot[];                            // n_crows x 3 when it fits
+    const uint32_t lane = threadIdx.x & 31u, slots = T.m_mask + 1, slots_round = (slots + 31u) & ~31u;
+    const uint32_t nr = T.n_crows < rows ? T.n_crows : rows;
+    const bool use_smem = nr * 24u <= 48u * 1024u;
+    if (use_smem) { for (uint32_t i = threadIdx.x; i < nr * 3u; i += blockDim.x) tot[i] = 0ull; __syncthreads(); }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < slots_round; i += gridDim.x * blockDim.x) {
+        const unsigned long long k = i < slots ? T.m_keys[i] : 0ull;
+        const unsigned long long c = k ? T.m_counts[i] : 0ull;
+        const uint32_t crow = (uint32_t)(k >> 48) & 0x3fffu, act = (uint32_t)(k >> 62) - 1u;
+        const bool has = k != 0ull && c != 0ull && crow < nr && act < 3u;
+        const uint32_t idx = has ? crow * 3u + act : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, idx);
+        const uint32_t s0 = __reduce_add_sync(peers, (uint32_t)c & 0x3fffffu);
+        const uint32_t s1 = __reduce_add_sync(peers, (uint32_t)(c >> 22) & 0x3fffffu);
+        const uint32_t s2 = __reduce_add_sync(peers, (uint32_t)(c >> 44));
+        if (has && (int)lane == __ffs(peers) - 1) {
+            const unsigned long long sum = (unsigned long long)s0 + ((unsigned long long)s1 << 22) + ((unsigned long long)s2 << 44);
+            if (use_smem) atomicAdd(&tot[idx], sum); else atomicAdd((unsigned long long *)&block[crow].count[act], sum);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nr * 3u; i += blockDim.x) if (tot[i]) atomicAdd((unsigned long long *)&block[i / 3u].count[i % 3u], tot[i]);
+    }
+    if (blockIdx.x == 0) for (uint32_t r = threadIdx.x; r < nr; r += blockDim.x) block[r].cgroup_id = T.crows[r].cgroup_id;
+}
 __global__ void k_counters_clear(const __grid_constant__ DevTables T)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.m_mask; i += gridDim.x * blockDim.x) { T.m_keys[i] = 0ull; T.m_counts[i] = 0ull; }
@@ -1083,6 +1123,12 @@ static int sm_count()
     return g_sm_count;
 }
 
+// SMs the persistent classify kernels leave free (clk_cfg.reserved_sms), so that the counter totals / export /
+// NCCL all-gather / import of batch k (side stream) run beside the classify kernel of batch k+1 instead of
+// delaying its CTAs: a classify CTA owns a whole SM (64 K registers), nothing can co-reside with it.
+static int reserved_sms(const DevTables &T) { int cap = sm_count() / 2, r = (int)T.reserved_sms; return r > cap ? cap : r; }
+static int side_grid(const DevTables &T, int want) { int r = reserved_sms(T); return r > 0 ? (r * 8 < want ? r * 8 : want) : want; }   // 256-thread CTAs, 8 per SM
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1098,7 +1144,7 @@ static encode_tiled_fn get_encode()
 }
 
 template <typename K>
-static cudaError_t occupancy_grid(K kernel, int threads, size_t smem, int *grid)
+static cudaError_t occupancy_grid(const DevTables &T, K kernel, int threads, size_t smem, int *grid)
 {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1106,7 +1152,7 @@ static cudaError_t occupancy_grid(K kernel, int threads, size_t smem, int *grid)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    *grid = per_sm * sm_count();
+    *grid = per_sm * (sm_count() - reserved_sms(T));              // persistent kernels leave the reserved SMs to the collective
     return cudaSuccess;
 }
 
@@ -1121,7 +1167,7 @@ static const char *launch_fast(const DevTables &T, const CUtensorMap &map, const
     while (agg_slots < 2048 && smem_layout(T, FAST_WARPS * kStages * WTILE_BYTES, FAST_WARPS * WQ_CAP * 4, FAST_WARPS * kStages, agg_slots * 2, FAST_WARPS).total <= budget) agg_slots *= 2;
     if (const char *s = getenv("CLK_AGG_SLOTS")) { uint32_t v = (uint32_t)atoi(s); if (v >= 64 && (v & (v - 1)) == 0) agg_slots = v; }
     SmemLayout L = smem_layout(T, FAST_WARPS * kStages * WTILE_BYTES, FAST_WARPS * WQ_CAP * 4, FAST_WARPS * kStages, agg_slots, FAST_WARPS);
-    if ((e = occupancy_grid(k_slots_fast<kStages, kSwizzle, kMinBlocks, kAllStaged>, FAST_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
+    if ((e = occupancy_grid(T, k_slots_fast<kStages, kSwizzle, kMinBlocks, kAllStaged>, FAST_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long n_cta = ((n + 31) / 32 + FAST_WARPS - 1) / FAST_WARPS;
     if ((unsigned long long)grid > n_cta) grid = (int)n_cta;
     k_slots_fast<kStages, kSwizzle, kMinBlocks, kAllStaged><<<grid, FAST_WARPS * 32, L.total, st>>>(T, map, (const uint8_t *)d_pkts, stride, rare_q, rare_cnt, agg_slots, n, flags, d_verdicts);
@@ -1138,7 +1184,7 @@ const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride
     int grid = 0;
     if (loader == LOADER_DIRECT || (flags & CLK_F_NAME_STAGE) || n >= 0x7fffffffull || stride > 0xffff0u) {
         SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
-        if ((e = occupancy_grid(k_generic<false>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
+        if ((e = occupancy_grid(T, k_generic<false>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
         unsigned long long need = (n + 255) / 256; if ((unsigned long long)grid > need) grid = (int)need;
         k_generic<false><<<grid, 256, L.total, st>>>(T, (const uint8_t *)d_pkts, nullptr, stride, n, flags, d_verdicts);
         if (info) { info->grid = grid; info->block = 256; info->smem = L.total; }
@@ -1178,7 +1224,7 @@ const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t
     int grid = 0; cudaError_t e;
     if (n < 0x7fffffffull && !getenv("CLK_VARLEN_GENERIC")) {
         SmemLayout L = smem_layout(T, 0, VL_WARPS * VL_QUEUES * VL_QCAP * 8, 0, MSLOTS, VL_WARPS);
-        if ((e = occupancy_grid(k_varlen_fast, VL_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
+        if ((e = occupancy_grid(T, k_varlen_fast, VL_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
         unsigned long long need = ((n + 31) / 32 + VL_WARPS - 1) / VL_WARPS; if ((unsigned long long)grid > need) grid = (int)need;
         k_varlen_fast<<<grid, VL_WARPS * 32, L.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, n, flags, d_verdicts);
         if (info) { info->grid = grid; info->block = VL_WARPS * 32; info->smem = L.total; }
@@ -1186,7 +1232,7 @@ const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t
         return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
     }
     SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
-    if ((e = occupancy_grid(k_generic<true>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
+    if ((e = occupancy_grid(T, k_generic<true>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long need = (n + 255) / 256; if ((unsigned long long)grid > need) grid = (int)need;
     k_generic<true><<<grid, 256, L.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, 0, n, flags, d_verdicts);
     if (info) { info->grid = grid; info->block = 256; info->smem = L.total; }
@@ -1200,7 +1246,7 @@ const char *launch_events(const DevTables &T, const clk_event *d_ev, unsigned lo
     if (n == 0) return nullptr;
     int grid = 0; cudaError_t e;
     SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
-    if ((e = occupancy_grid(k_events, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
+    if ((e = occupancy_grid(T, k_events, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
     unsigned long long need = (n + 255) / 256; if ((unsigned long long)grid > need) grid = (int)need;
     k_events<<<grid, 256, L.total, st>>>(T, d_ev, n, flags, d_verdicts);
     if (info) { info->grid = grid; info->block = 256; info->smem = L.total; }
@@ -1227,12 +1273,21 @@ const char *launch_counters_export(const DevTables &T, clk_metric *d_block, uint
 {
     cudaError_t e = cudaMemsetAsync(d_block, 0, sizeof(clk_metric), st);
     if (e != cudaSuccess) return cudaGetErrorString(e);
-    k_counters_export<<<sm_count() * 8, 256, 0, st>>>(T, d_block, cap_rows);
+    k_counters_export<<<side_grid(T, sm_count() * 8), 256, 0, st>>>(T, d_block, cap_rows);
+    e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+const char *launch_counters_totals(const DevTables &T, clk_total *d_block, uint32_t rows, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(d_block, 0, (size_t)rows * sizeof(clk_total), st);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    const uint32_t nr = T.n_crows < rows ? T.n_crows : rows;
+    const size_t smem = nr * 24u <= 48u * 1024u ? nr * 24u : 0;
+    k_counters_totals<<<side_grid(T, sm_count() * 4), 256, smem, st>>>(T, d_block, rows);
     e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 const char *launch_counters_clear(const DevTables &T, cudaStream_t st)
 {
-    k_counters_clear<<<sm_count() * 8, 256, 0, st>>>(T);
+    k_counters_clear<<<side_grid(T, sm_count() * 8), 256, 0, st>>>(T);
     cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 const char *launch_counters_import(const DevTables &T, const clk_metric *d_blocks, uint32_t n_blocks, uint32_t block_rows, cudaStream_t st)
@@ -1240,7 +1295,7 @@ const char *launch_counters_import(const DevTables &T, const clk_metric *d_block
     unsigned long long blocks = ((unsigned long long)n_blocks * block_rows + 255) / 256;   // one row per thread: the adds are L2-latency bound
     if (blocks > (unsigned long long)sm_count() * 64) blocks = (unsigned long long)sm_count() * 64;
     if (blocks < 1) blocks = 1;
-    k_counters_import<<<(int)blocks, 256, 0, st>>>(T, d_blocks, n_blocks, block_rows);
+    k_counters_import<<<side_grid(T, (int)blocks), 256, 0, st>>>(T, d_blocks, n_blocks, block_rows);
     cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

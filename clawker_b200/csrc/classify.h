@@ -21,6 +21,7 @@ const char *launch_dns_extract(const DevTables &T, const void *d_pkts, const uin
                                const uint32_t *d_verdicts, unsigned long long *d_block_sums, unsigned long long *d_pos,
                                unsigned long long *d_total, clk_dns_update_rec *d_out, unsigned long long cap, cudaStream_t st);
 const char *launch_counters_export(const DevTables &T, clk_metric *d_block, uint32_t cap_rows, cudaStream_t st);
+const char *launch_counters_totals(const DevTables &T, clk_total *d_block, uint32_t rows, cudaStream_t st);
 const char *launch_counters_clear(const DevTables &T, cudaStream_t st);
 const char *launch_counters_import(const DevTables &T, const clk_metric *d_blocks, uint32_t n_blocks, uint32_t block_rows, cudaStream_t st);
 

@@ -136,6 +136,7 @@ struct DevTables {
     uint32_t m_max;                                      // max_entries of metrics_map (common.h:173): inserts beyond it are dropped
     // sizes for optional shared-memory staging (bytes; 0 = do not stage)
     uint32_t stage_ep_bytes, stage_soa_bytes, stage_dns_bytes, stage_route_bytes, stage_pre_bytes, stage_ep6_bytes;
+    uint32_t reserved_sms;                               // SMs the persistent classify kernels leave to the side-stream collective (clk_cfg)
 };
 
 }  // namespace clk

@@ -67,7 +67,7 @@ struct clk_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t pipe[3] = { nullptr, nullptr, nullptr };
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    uint32_t max_containers = 256, max_dns = 16384, max_routes = 8192, max_metrics = 16384, max_cidrs = 1u << 20;
+    uint32_t max_containers = 256, max_dns = 16384, max_routes = 8192, max_metrics = 16384, max_cidrs = 1u << 20, reserved_sms = 0;
 
     // host shadow tables (the BPF maps)
     std::unordered_map<uint64_t, clk_container_config> container;
@@ -89,6 +89,7 @@ struct clk_engine {
     DevTables T;                                                         // active snapshot
     DevBuf m_keys, m_counts, m_dropped;      // this GPU's metrics_map (kernels write)
     DevBuf g_keys, g_counts, g_dropped;      // merged view after the all-gather (clk_counters_import)
+    uint32_t g_mask = 0;                       // its slot mask: sized for n_blocks full tables at load <= 1/2
     DevBuf work_rare[4];                       // rare-frame queues: [0..2] host pipeline lanes, [3] the *_dev entry
     DevBuf work_pkts[3], work_offs[3], work_verd[3], scan_sums, scan_pos, scan_total, upd_out, ctr_block;
     clk_stats stats;
@@ -110,7 +111,11 @@ int fail(clk_engine *e, int code, const char *fmt, ...)
     return code;
 }
 #define CUDA_TRY(e, call) do { cudaError_t _c = (call); if (_c != cudaSuccess) return fail((e), CLK_EIO, "%s: %s", #call, cudaGetErrorString(_c)); } while (0)
-#define NEED_GPU(e) do { if ((e)->host_only) return fail((e), CLK_ENOSYS, "engine was created host-only (no CUDA device): classification requires the GPU"); } while (0)
+// Every GPU entry point runs on the engine's device whatever the calling thread's current device is (a host with
+// one engine per GPU calls from arbitrary threads; streams and buffers of another device are "invalid resource handle").
+#define NEED_GPU(e) do { if ((e)->host_only) return fail((e), CLK_ENOSYS, "engine was created host-only (no CUDA device): classification requires the GPU"); \
+                         cudaError_t _d = cudaSetDevice((e)->device); if (_d != cudaSuccess) return fail((e), CLK_EIO, "cudaSetDevice(%d): %s", (e)->device, cudaGetErrorString(_d)); \
+                         (void)cudaGetLastError(); /* a stale error left by another library on this thread is not ours to report */ } while (0)
 
 struct MapSpec { size_t klen, vlen; };
 const MapSpec kSpecs[CLK_MAP__COUNT] = {
@@ -370,7 +375,7 @@ int publish_locked(clk_engine *e)
     }
     std::sort(T.coredns_ips, T.coredns_ips + T.n_coredns);
     T.m_keys = (unsigned long long *)e->m_keys.p; T.m_counts = (unsigned long long *)e->m_counts.p;
-    T.m_mask = e->T.m_mask; T.m_dropped = (unsigned long long *)e->m_dropped.p; T.m_max = e->max_metrics;
+    T.m_mask = e->T.m_mask; T.m_dropped = (unsigned long long *)e->m_dropped.p; T.m_max = e->max_metrics; T.reserved_sms = e->reserved_sms;
     // shared-memory staging budget: endpoints <= 256 rows, dns <= 32 KiB, route <= 8 KiB
     if (e->stage_tables) {
         if (n_ep4 && rows.size() <= 256) { T.stage_ep_bytes = (uint32_t)ep_slots.size() * 8; T.stage_soa_bytes = (uint32_t)rowq.size() * 16; }
@@ -424,6 +429,7 @@ int clk_engine_create(const clk_cfg *cfg, clk_engine **out)
         if (cfg->max_metrics) e->max_metrics = cfg->max_metrics;
         if (cfg->max_cidrs) e->max_cidrs = cfg->max_cidrs;
         e->host_only = (cfg->flags & 1u) != 0;
+        e->reserved_sms = cfg->reserved_sms;
     }
     if (const char *s = getenv("CLK_LOADER")) e->loader = atoi(s);
     if (const char *s = getenv("CLK_STAGE")) e->stage_tables = atoi(s) != 0;
@@ -838,10 +844,50 @@ int clk_counters_export(clk_engine *e, void *d_block, void *stream)
     return CLK_OK;
 }
 
+int clk_totals_rows(clk_engine *e, uint32_t *rows)
+{
+    if (!e || !rows) return fail(e, CLK_EINVAL, "NULL");
+    *rows = e->max_containers;
+    return CLK_OK;
+}
+
+int clk_totals_export(clk_engine *e, void *d_block, void *stream)
+{
+    if (!e || !d_block) return fail(e, CLK_EINVAL, "NULL");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    const char *err = launch_counters_totals(e->T, (clk_total *)d_block, e->max_containers, stream ? (cudaStream_t)stream : e->stream);
+    if (err) return fail(e, CLK_EIO, "totals export: %s", err);
+    e->stats.kernel_launches++;
+    return CLK_OK;
+}
+
+int clk_totals_merge(clk_engine *e, const void *d_blocks, uint32_t n_blocks, clk_total *out, uint32_t cap, uint32_t *n)
+{
+    if (!e || !d_blocks || !n || (cap && !out)) return fail(e, CLK_EINVAL, "NULL");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    std::vector<clk_total> rows((size_t)n_blocks * e->max_containers);
+    if (!rows.empty()) CUDA_TRY(e, cudaMemcpy(rows.data(), d_blocks, rows.size() * sizeof(clk_total), cudaMemcpyDeviceToHost));
+    std::map<uint64_t, clk_total> sum;
+    for (const clk_total &r : rows) {
+        if (r.cgroup_id == 0 && !(r.count[0] | r.count[1] | r.count[2])) continue;
+        clk_total &t = sum[r.cgroup_id]; t.cgroup_id = r.cgroup_id;
+        for (int a = 0; a < 3; a++) t.count[a] += r.count[a];
+    }
+    *n = (uint32_t)sum.size();
+    uint32_t k = 0;
+    for (auto &kv : sum) { if (k >= cap) break; out[k++] = kv.second; }
+    return CLK_OK;
+}
+
 static DevTables global_view(clk_engine *e)
 {
     DevTables G = e->T;
-    G.m_keys = (unsigned long long *)e->g_keys.p; G.m_counts = (unsigned long long *)e->g_counts.p; G.m_dropped = (unsigned long long *)e->g_dropped.p; G.m_max = 0xffffffffu;
+    G.m_keys = (unsigned long long *)e->g_keys.p; G.m_counts = (unsigned long long *)e->g_counts.p; G.m_dropped = (unsigned long long *)e->g_dropped.p; G.m_max = 0xffffffffu; G.m_mask = e->g_mask;
     return G;
 }
 
@@ -852,7 +898,10 @@ int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, 
     std::lock_guard<std::mutex> g(e->mu);
     int rc = ensure_published(e); if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    const size_t slots = (size_t)e->T.m_mask + 1;
+    size_t slots = (size_t)e->T.m_mask + 1;                     // every rank may contribute max_entries distinct keys
+    while (slots < 2 * (size_t)n_blocks * ((size_t)e->max_metrics + 1) && slots < ((size_t)1 << 31)) slots <<= 1;
+    if (slots - 1 > e->g_mask) e->g_mask = (uint32_t)(slots - 1);
+    slots = (size_t)e->g_mask + 1;
     CUDA_TRY(e, e->g_keys.ensure(slots * 8)); CUDA_TRY(e, e->g_counts.ensure(slots * 8)); CUDA_TRY(e, e->g_dropped.ensure(16));
     DevTables G = global_view(e);
     const char *err = launch_counters_clear(G, st);
@@ -871,9 +920,9 @@ static int counters_read_impl(clk_engine *e, bool global, clk_metric *out, uint3
     if (global && !e->g_keys.p) { *n = 0; return CLK_OK; }
     CUDA_TRY(e, cudaSetDevice(e->device));
     CUDA_TRY(e, cudaDeviceSynchronize());
-    uint32_t rows = e->T.m_mask + 2;                            // header + every slot (the merged view may hold more than max_entries)
-    CUDA_TRY(e, e->ctr_block.ensure((size_t)rows * sizeof(clk_metric)));
     DevTables V = global ? global_view(e) : e->T;
+    uint32_t rows = V.m_mask + 2;                               // header + every slot (the merged view may hold more than max_entries)
+    CUDA_TRY(e, e->ctr_block.ensure((size_t)rows * sizeof(clk_metric)));
     const char *err = launch_counters_export(V, (clk_metric *)e->ctr_block.p, rows, e->stream);
     if (err) return fail(e, CLK_EIO, "counters export: %s", err);
     e->stats.kernel_launches++;

@@ -83,6 +83,9 @@ def lib() -> C.CDLL:
         "clk_counters_block_rows": (i32, [vp, C.POINTER(u32)]),
         "clk_counters_export": (i32, [vp, vp, vp]),
         "clk_counters_import": (i32, [vp, vp, u32, vp]),
+        "clk_totals_rows": (i32, [vp, C.POINTER(u32)]),
+        "clk_totals_export": (i32, [vp, vp, vp]),
+        "clk_totals_merge": (i32, [vp, vp, u32, vp, u32, C.POINTER(u32)]),
         "clk_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "clk_sync": (i32, [vp]),
         "clk_host_alloc": (i32, [sz, C.POINTER(vp)]),
@@ -101,7 +104,7 @@ EXPORTS = ["clk_abi_version", "clk_strerror", "clk_last_error", "clk_engine_crea
            "clk_cidr_to_addr_mask", "clk_rules_compile", "clk_rules_dump", "clk_publish", "clk_classify_slots",
            "clk_classify_varlen", "clk_classify_slots_dev", "clk_classify_varlen_dev", "clk_classify_events",
            "clk_dns_answers", "clk_counters_read", "clk_counters_read_global", "clk_counters_reset", "clk_counters_block_rows",
-           "clk_counters_export", "clk_counters_import", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
+           "clk_counters_export", "clk_counters_import", "clk_totals_rows", "clk_totals_export", "clk_totals_merge", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
 
 
 def pinned_empty(nbytes: int) -> np.ndarray:
@@ -133,10 +136,10 @@ class Engine:
     """One GPU's classifier instance (clk_engine)."""
 
     def __init__(self, device: int = -1, host_only: bool = False, max_containers: int = 0, max_dns_cache: int = 0,
-                 max_routes: int = 0, max_metrics: int = 0, max_cidrs: int = 0):
+                 max_routes: int = 0, max_metrics: int = 0, max_cidrs: int = 0, reserved_sms: int = 0):
         self.L = lib()
-        cfg = Cfg(abi.OK + 1, device, max_containers, max_dns_cache, max_routes, max_metrics, max_cidrs, 1 if host_only else 0)
-        cfg.abi_version = self.L.clk_abi_version()
+        cfg = Cfg(self.L.clk_abi_version(), device, max_containers, max_dns_cache, max_routes, max_metrics, max_cidrs,
+                  1 if host_only else 0, reserved_sms)
         h = C.c_void_p()
         rc = self.L.clk_engine_create(C.byref(cfg), C.byref(h))
         if rc:
@@ -299,6 +302,22 @@ class Engine:
 
     def counters_import(self, d_blocks: int, n_blocks: int, stream: int = 0):
         self._ck(self.L.clk_counters_import(self.h, d_blocks, n_blocks, stream or None))
+
+    # per-batch form of the collective: dense per-container totals (rows x 32 B)
+    def totals_rows(self) -> int:
+        n = C.c_uint32()
+        self._ck(self.L.clk_totals_rows(self.h, C.byref(n)))
+        return n.value
+
+    def totals_export(self, d_block: int, stream: int = 0):
+        self._ck(self.L.clk_totals_export(self.h, d_block, stream or None))
+
+    def totals_merge(self, d_blocks: int, n_blocks: int) -> np.ndarray:
+        """Sum gathered clk_total blocks by cgroup_id (synchronises the device); rows sorted by cgroup_id."""
+        out = np.zeros(n_blocks * self.totals_rows(), dtype=abi.TOTAL_DTYPE)
+        n = C.c_uint32()
+        self._ck(self.L.clk_totals_merge(self.h, d_blocks, n_blocks, out.ctypes.data, out.shape[0], C.byref(n)))
+        return out[:n.value]
 
     def stats(self) -> Stats:
         s = Stats()

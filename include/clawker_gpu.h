@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CLK_ABI_VERSION 1
+#define CLK_ABI_VERSION 2
 
 /* ---- error codes (negative errno style; ENOENT mirrors ebpf.ErrKeyNotExist,
  *      internal/ebpf/manager.go:222-231) ------------------------------------ */
@@ -136,6 +136,8 @@ typedef struct clk_cfg {
     uint32_t max_metrics;
     uint32_t max_cidrs;          /* 0 = 1<<20                                              */
     uint32_t flags;              /* CLK_CFG_*                                              */
+    uint32_t reserved_sms;       /* SMs the persistent classify kernels leave free for the side-stream
+                                    counters collective (multi-GPU hosts; 0 = use every SM)          */
 } clk_cfg;
 
 /* Host-only engine: tables, rule compiler and map ops work without a CUDA device (control-plane
@@ -334,6 +336,20 @@ int clk_counters_block_rows(clk_engine *e, uint32_t *rows);
 int clk_counters_read_global(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n);
 int clk_counters_export(clk_engine *e, void *d_block, void *stream);
 int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, void *stream);
+
+/* Per-batch form of the same collective: dense per-container totals of the local table, one
+ * clk_total per container_map row (`rows` = max_containers, unused rows zero) in a caller-provided
+ * DEVICE buffer — 32 B per container instead of 24 B per metrics_map row, so it is cheap enough to
+ * all-gather after every batch; the per-key merge above then runs only when somebody reads it.
+ * clk_totals_merge sums `n_blocks` gathered blocks by cgroup_id into host rows sorted by cgroup_id
+ * (synchronises the device). */
+typedef struct clk_total {
+    uint64_t cgroup_id;
+    uint64_t count[3];                  /* indexed by CLK_ACTION_ALLOW / DENY / BYPASS */
+} clk_total;                            /* 32 B */
+int clk_totals_rows(clk_engine *e, uint32_t *rows);
+int clk_totals_export(clk_engine *e, void *d_block, void *stream);
+int clk_totals_merge(clk_engine *e, const void *d_blocks, uint32_t n_blocks, clk_total *out, uint32_t cap, uint32_t *n);
 
 /* ---- introspection for benches ------------------------------------------------ */
 typedef struct clk_stats {

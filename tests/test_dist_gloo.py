@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from clawker_b200 import capture, sharding
-from clawker_b200.abi import METRIC_DTYPE
+from clawker_b200.abi import METRIC_DTYPE, TOTAL_DTYPE
 from oracle import oracle
 
 from util import assert_same_metrics, oracle_tables
@@ -39,9 +39,13 @@ def _worker(rank, world, port, q):
     out = [torch.empty_like(blk) for _ in range(world)]
     dist.all_gather(out, blk)                                 # the one collective
     merged = sharding.merge_blocks(np.stack([o.numpy().view(METRIC_DTYPE) for o in out]))
+    tb = torch.from_numpy(sharding.totals_of(met, 16).view(np.uint8).copy())          # the per-batch totals block
+    tout = [torch.empty_like(tb) for _ in range(world)]
+    dist.all_gather(tout, tb)
+    totals = sharding.merge_totals(np.stack([o.numpy().view(TOTAL_DTYPE) for o in tout]))
     vt = [None] * world
     dist.all_gather_object(vt, (lo, hi, verd))
-    q.put((rank, merged, vt))
+    q.put((rank, merged, vt, totals))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -60,8 +64,10 @@ def test_two_rank_shards_and_counter_allgather():
     w = capture.make_workload("c2")
     pk = capture.gen_slots(w, N, seed=4)
     want_v, want_m = oracle.Oracle("port").load(oracle_tables(w)).classify(pk)
-    for rank, merged, vt in res:
+    want_t = sharding.merge_totals(sharding.totals_of(want_m, 16))
+    for rank, merged, vt, totals in res:
         assert_same_metrics(merged, want_m, f"rank {rank} merged view")          # every rank ends with the same sum
+        assert np.array_equal(totals, want_t) and int(totals["count"].sum()) == int(want_m["count"].sum())
         got = np.concatenate([v for _, _, v in sorted(vt, key=lambda t: t[0])])
         assert np.array_equal(got, want_v)                                        # verdicts independent of the sharding
 
@@ -83,3 +89,17 @@ def test_merge_blocks_sums_by_key():
     assert m.size == 2 and int(m["count"].sum()) == 23
     with pytest.raises(ValueError):
         sharding.rows_to_block(np.zeros(5, dtype=METRIC_DTYPE), 4)
+
+
+def test_totals_blocks():
+    a = np.zeros(4, dtype=METRIC_DTYPE)
+    a[0] = (7, 2, 3, 0, 0, 5)
+    a[1] = (7, 9, 3, 1, 0, 7)
+    a[2] = (9, 2, 3, 2, 0, 1)
+    a[3] = (7, 4, 4, 0, 0, 2)
+    t = sharding.totals_of(a, 8)
+    assert t["cgroup_id"][:2].tolist() == [7, 9] and t["count"][0].tolist() == [7, 7, 0] and t["count"][1].tolist() == [0, 0, 1]
+    m = sharding.merge_totals(np.stack([t, t]))
+    assert m.size == 2 and m["count"][0].tolist() == [14, 14, 0]
+    with pytest.raises(ValueError):
+        sharding.totals_of(a, 1)

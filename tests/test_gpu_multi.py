@@ -24,8 +24,11 @@ def _worker(rank, world, port, q):
     lo, hi = sharding.shard_range(N, rank, world)
     e = make_engine(w, device=rank, max_metrics=1 << 18)
     verd = e.classify_slots(pk[lo:hi])
-    sharding.allgather_counters(e)
-    q.put((rank, lo, hi, verd, e.counters(merged=True), e.counters()))
+    tg = sharding.TotalsGather(e)
+    tg.enqueue()                                              # per-batch form: dense per-container totals
+    totals = tg.read()
+    sharding.allgather_counters(e)                            # on-read form: per-key merge
+    q.put((rank, lo, hi, verd, e.counters(merged=True), e.counters(), totals))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -34,7 +37,7 @@ def test_two_gpu_shards_and_nccl_counter_allgather():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    from clawker_b200 import capture
+    from clawker_b200 import capture, sharding
     from oracle import oracle
     from util import assert_same_metrics, oracle_tables
     s = socket.socket()
@@ -54,6 +57,9 @@ def test_two_gpu_shards_and_nccl_counter_allgather():
     pk = capture.gen_slots(w, N, seed=4)
     want_v, want_m = oracle.Oracle("port").load(oracle_tables(w)).classify(pk)
     assert np.array_equal(np.concatenate([r[3] for r in res]), want_v)
-    for rank, lo, hi, verd, merged, local in res:
+    want_t = sharding.merge_totals(sharding.totals_of(want_m, 256))
+    for rank, lo, hi, verd, merged, local, totals in res:
         assert_same_metrics(merged, want_m, f"rank {rank} merged")
+        totals = totals[totals["count"].sum(axis=1) > 0]                     # containers without traffic have all-zero rows
+        assert np.array_equal(totals, want_t), f"rank {rank} totals"
         assert int(local["count"].sum()) < int(merged["count"].sum())

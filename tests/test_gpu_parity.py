@@ -22,6 +22,57 @@ def test_c2_slots_all_loaders(loader):
     assert e.stats().metrics_dropped == 0
 
 
+@pytest.mark.parametrize("reserved", [0, 6])
+def test_per_container_totals_and_reserved_sms(reserved):
+    """clk_totals_export == the local metrics_map grouped by (container, action); classification is independent of
+    how many SMs the persistent kernel leaves to the side stream."""
+    import torch
+    from clawker_b200 import sharding
+    w = capture.make_workload("c2")
+    pk = capture.gen_slots(w, 250_003, seed=12, v6_frac=0.03)
+    want, wm = oracle.Oracle("port").load(oracle_tables(w)).classify(pk)
+    e = make_engine(w, device=0, reserved_sms=reserved, max_containers=64)
+    assert_same_verdicts(e.classify_slots(pk), want, f"reserved {reserved}")
+    assert e.stats().last_grid <= e.stats().sm_count - reserved
+    assert_same_metrics(e.counters(), wm, f"reserved {reserved}")
+    blk = torch.zeros(2 * e.totals_rows() * abi.TOTAL_DTYPE.itemsize, dtype=torch.uint8, device="cuda:0")
+    half = e.totals_rows() * abi.TOTAL_DTYPE.itemsize
+    torch.cuda.synchronize()                                      # blk is zero-filled on torch's stream, the export runs on the engine's
+    e.totals_export(blk.data_ptr())
+    e.sync()
+    blk[half:] = blk[:half]                                       # two identical "ranks"
+    got = e.totals_merge(blk.data_ptr(), 2)
+    got = got[got["count"].sum(axis=1) > 0]                       # containers without traffic have all-zero rows
+    wt = sharding.merge_totals(sharding.totals_of(wm, 64))
+    assert np.array_equal(got["cgroup_id"], wt["cgroup_id"]) and np.array_equal(got["count"], 2 * wt["count"])
+
+
+def test_metrics_map_full_is_strict():
+    """metrics_map max_entries (common.h:173): a full map refuses new keys (BPF_NOEXIST insert fails, metric_inc
+    common.h:206-209) — never more than max_entries rows, existing keys keep counting, nothing is lost silently."""
+    w = capture.make_workload("c2")
+    pk = capture.gen_slots(w, 400_000, seed=21)
+    _, wm = oracle.Oracle("port").load(oracle_tables(w)).classify(pk)
+    cap = 1000
+    assert wm.size > 4 * cap
+    e = make_engine(w, device=0, max_metrics=cap)
+    e.classify_slots(pk)
+    got = e.counters()
+    assert 0 < got.size <= cap
+    assert int(got["count"].sum()) + e.stats().metrics_dropped == int(wm["count"].sum())
+    want = {(int(r["cgroup_id"]), int(r["domain_hash"]), int(r["dst_port"]), int(r["action"])): int(r["count"]) for r in wm}
+    for r in got:                                                 # a key that got in counts every one of its increments... or fewer, never more
+        k = (int(r["cgroup_id"]), int(r["domain_hash"]), int(r["dst_port"]), int(r["action"]))
+        assert k in want and 0 < int(r["count"]) <= want[k]
+    import torch
+    blk = torch.zeros(e.counters_block_rows() * 24, dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    e.counters_export(blk.data_ptr())                             # the collective's block holds every row of a full map
+    e.sync()
+    rows = blk.cpu().numpy().view(abi.METRIC_DTYPE)
+    assert int(rows[0]["count"]) == got.size
+
+
 def test_c2_vs_reference_object():
     """No CIDR rules -> the decision stage must equal the reference's own eBPF C."""
     if not oracle.have_ref():
