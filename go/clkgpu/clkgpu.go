@@ -49,6 +49,7 @@ type Engine struct{ h *C.clk_engine }
 type Config struct {
 	Device                                                         int
 	MaxContainers, MaxDNSCache, MaxRoutes, MaxMetrics, MaxCIDRs uint32
+	ReservedSMs                                                    uint32 // SMs left to the side-stream collective (multi-GPU hosts)
 }
 
 func (e *Engine) err(rc C.int) error {
@@ -68,7 +69,7 @@ func (e *Engine) err(rc C.int) error {
 func New(cfg Config) (*Engine, error) {
 	c := C.clk_cfg{abi_version: C.CLK_ABI_VERSION, device: C.int32_t(cfg.Device),
 		max_containers: C.uint32_t(cfg.MaxContainers), max_dns_cache: C.uint32_t(cfg.MaxDNSCache),
-		max_routes: C.uint32_t(cfg.MaxRoutes), max_metrics: C.uint32_t(cfg.MaxMetrics), max_cidrs: C.uint32_t(cfg.MaxCIDRs)}
+		max_routes: C.uint32_t(cfg.MaxRoutes), max_metrics: C.uint32_t(cfg.MaxMetrics), max_cidrs: C.uint32_t(cfg.MaxCIDRs), reserved_sms: C.uint32_t(cfg.ReservedSMs)}
 	var h *C.clk_engine
 	if rc := C.clk_engine_create(&c, &h); rc != C.CLK_OK {
 		return nil, fmt.Errorf("clawker_gpu: %s (%d)", C.GoString(C.clk_last_error(nil)), int(rc))
@@ -204,5 +205,39 @@ func (e *Engine) CountersRead() ([]Metric, error) {
 	}
 	out := make([]Metric, int(n))
 	err := e.err(C.clk_counters_read(e.h, (*C.clk_metric)(unsafe.Pointer(&out[0])), n, &n))
+	return out[:int(n)], err
+}
+
+// Total mirrors clk_total: one container's ALLOW / DENY / BYPASS sums.
+type Total struct {
+	CgroupID uint64
+	Count    [3]uint64
+}
+
+// TotalsRows is the fixed row count of a totals block (max_containers).
+func (e *Engine) TotalsRows() (uint32, error) {
+	var n C.uint32_t
+	err := e.err(C.clk_totals_rows(e.h, &n))
+	return uint32(n), err
+}
+
+// TotalsExport writes this GPU's per-container totals into a device block (TotalsRows x 32 B) on `stream`;
+// the caller all-gathers the blocks (ncclAllGather) and hands them to TotalsMerge.
+func (e *Engine) TotalsExport(dBlock, stream unsafe.Pointer) error {
+	return e.err(C.clk_totals_export(e.h, dBlock, stream))
+}
+
+// TotalsMerge sums nBlocks gathered device blocks by cgroup id.
+func (e *Engine) TotalsMerge(dBlocks unsafe.Pointer, nBlocks uint32) ([]Total, error) {
+	rows, err := e.TotalsRows()
+	if err != nil {
+		return nil, err
+	}
+	out := make([]Total, int(rows*nBlocks))
+	var n C.uint32_t
+	if len(out) == 0 {
+		return nil, nil
+	}
+	err = e.err(C.clk_totals_merge(e.h, dBlocks, C.uint32_t(nBlocks), (*C.clk_total)(unsafe.Pointer(&out[0])), C.uint32_t(len(out)), &n))
 	return out[:int(n)], err
 }
