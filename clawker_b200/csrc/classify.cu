@@ -348,20 +348,20 @@ struct MetricAgg {
 
 // Two probes at most: keys that find a slot early (the frequent ones, by construction) stay in shared
 // memory for the CTA's lifetime; everything else goes to the device table.
-__device__ __forceinline__ void metric_cta_add(const DevTables &T, MetricAgg &ag, unsigned long long key, unsigned int cnt)
+__device__ __forceinline__ bool metric_cta_try(MetricAgg &ag, unsigned long long key, unsigned int cnt)
 {
     uint32_t h = mhash(key) & ag.mask;
     #pragma unroll
     for (int p = 0; p < 2; p++) {
         unsigned long long cur = ag.keys[h];
         if (cur == 0ull) cur = atomicCAS(&ag.keys[h], 0ull, key);
-        if (cur == 0ull || cur == key) { atomicAdd(&ag.counts[h], cnt); return; }
+        if (cur == 0ull || cur == key) { atomicAdd(&ag.counts[h], cnt); return true; }
         h = (h + 1) & ag.mask;
     }
-    ag.dropped += metric_global_add(T, key, cnt);
+    return false;
 }
 
-// Apply the first `take` (<= 32) log entries, one per lane.  All 32 lanes must call.
+// Apply the first `take` (<= 32) log entries to the device table, one per lane.  All 32 lanes must call.
 __device__ __forceinline__ void metric_log_apply(const DevTables &T, MetricAgg &ag, uint32_t take)
 {
     const uint32_t lane = threadIdx.x & 31u;
@@ -371,22 +371,32 @@ __device__ __forceinline__ void metric_log_apply(const DevTables &T, MetricAgg &
     __syncwarp();
     if (lane + 32 < ag.log_n) { ag.log_keys[lane] = k2; ag.log_cnts[lane] = c2; }
     ag.log_n -= take;
-    if (lane < take) metric_cta_add(T, ag, k, c);
+    if (lane < take) ag.dropped += metric_global_add(T, k, c);
     __syncwarp();
 }
 
-// All 32 lanes must call (tail lanes with has == false).
+// All 32 lanes must call (tail lanes with has == false).  Every lane adds its own increment to the CTA table
+// (shared-memory atomics serialise equal addresses in the memory pipe, not in the instruction stream); only the
+// increments that find no slot there are logged, and the log goes to the device table 32 entries at a time.
 __device__ __forceinline__ void metric_warp_emit(const DevTables &T, MetricAgg &ag, bool has, unsigned long long key)
 {
     const uint32_t lane = threadIdx.x & 31u;
+#ifdef CLK_METRIC_MATCH
     const unsigned m = __ballot_sync(0xffffffffu, has);
     if (m == 0) return;
     unsigned peers = 0;
     if (has) peers = __match_any_sync(m, key);
     const bool leader = has && (int)lane == __ffs(peers) - 1;
-    const unsigned lm = __ballot_sync(0xffffffffu, leader);
-    if (leader) { const uint32_t pos = ag.log_n + __popc(lm & ((1u << lane) - 1u)); ag.log_keys[pos] = key; ag.log_cnts[pos] = __popc(peers); }
-    ag.log_n += __popc(lm);
+    const unsigned int cnt = __popc(peers);
+    const bool miss = leader && !metric_cta_try(ag, key, cnt);
+#else
+    const unsigned int cnt = 1u;
+    const bool miss = has && !metric_cta_try(ag, key, 1u);
+#endif
+    const unsigned mm = __ballot_sync(0xffffffffu, miss);
+    if (mm == 0) return;
+    if (miss) { const uint32_t pos = ag.log_n + __popc(mm & ((1u << lane) - 1u)); ag.log_keys[pos] = key; ag.log_cnts[pos] = cnt; }
+    ag.log_n += __popc(mm);
     __syncwarp();
     if (ag.log_n >= 32) metric_log_apply(T, ag, 32);
 }
