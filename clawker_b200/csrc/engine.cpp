@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cerrno>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,8 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../../include/clawker_gpu.h"
 #include "classify.h"
@@ -949,6 +952,106 @@ int clk_counters_reset(clk_engine *e)
     if (err) return fail(e, CLK_EIO, "counters clear: %s", err);
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     e->stats.kernel_launches++;
+    return CLK_OK;
+}
+
+// ---- pinned state (the bpffs analogue) ------------------------------------------------
+namespace {
+const char kPinMagic[8] = { 'C', 'L', 'K', 'P', 'I', 'N', 1, 0 };
+struct PinWriter {
+    std::string b;
+    void raw(const void *p, size_t n) { b.append((const char *)p, n); }
+    void u32(uint32_t v) { raw(&v, 4); }
+    void u64(uint64_t v) { raw(&v, 8); }
+    void str(const std::string &s) { u32((uint32_t)s.size()); raw(s.data(), s.size()); }
+    void section(uint32_t tag, uint64_t count) { u32(tag); u64(count); }
+};
+struct PinReader {
+    const std::string &b; size_t p = 0; bool ok = true;
+    explicit PinReader(const std::string &s) : b(s) {}
+    bool raw(void *out, size_t n) { if (!ok || p + n > b.size()) { ok = false; memset(out, 0, n); return false; } memcpy(out, b.data() + p, n); p += n; return true; }
+    uint32_t u32() { uint32_t v; raw(&v, 4); return v; }
+    uint64_t u64() { uint64_t v; raw(&v, 8); return v; }
+    std::string str() { uint32_t n = u32(); if (!ok || p + n > b.size()) { ok = false; return ""; } std::string s(b.data() + p, n); p += n; return s; }
+};
+enum { PIN_END = 0, PIN_CONTAINER, PIN_BYPASS, PIN_DNS, PIN_ROUTE, PIN_EP, PIN_EP6, PIN_CIDR, PIN_ZONES, PIN_SNIS, PIN_MAPPINGS, PIN_CCIDRS };
+}  // namespace
+
+int clk_state_save(clk_engine *e, const char *path)
+{
+    if (!e || !path || !*path) return fail(e, CLK_EINVAL, "NULL");
+    PinWriter w;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        w.raw(kPinMagic, 8);
+        w.section(PIN_CONTAINER, e->container.size()); for (auto &kv : e->container) { w.u64(kv.first); w.raw(&kv.second, sizeof kv.second); }
+        w.section(PIN_BYPASS, e->bypass.size());       for (auto &kv : e->bypass) { w.u64(kv.first); w.raw(&kv.second, 1); }
+        w.section(PIN_DNS, e->dns.size());             for (auto &kv : e->dns) { w.u32(kv.first); w.raw(&kv.second, sizeof kv.second); }
+        w.section(PIN_ROUTE, e->route.size());         for (auto &kv : e->route) { w.u64(kv.first); w.raw(&kv.second, 2); }
+        w.section(PIN_EP, e->endpoint.size());         for (auto &kv : e->endpoint) { w.u32(kv.first); w.raw(&kv.second, sizeof kv.second); }
+        w.section(PIN_EP6, e->endpoint6.size());       for (auto &kv : e->endpoint6) { w.raw(kv.first.data(), 16); w.raw(&kv.second, sizeof kv.second); }
+        w.section(PIN_CIDR, e->cidr.size());           for (auto &kv : e->cidr) { w.u32(kv.first.first); w.u32(kv.first.second); }
+        w.section(PIN_ZONES, e->compiled.zones.size()); for (auto &z : e->compiled.zones) w.str(z);
+        w.section(PIN_SNIS, e->compiled.snis.size());   for (auto &z : e->compiled.snis) w.str(z);
+        w.section(PIN_MAPPINGS, e->compiled.mappings.size()); for (auto &m : e->compiled.mappings) { w.str(m.dst); w.u32((uint32_t)m.dst_port); w.u32((uint32_t)m.envoy_port); }
+        w.section(PIN_CCIDRS, e->compiled.cidrs.size()); for (auto &c : e->compiled.cidrs) { w.u32(c.first); w.u32(c.second); }
+        w.section(PIN_END, 0);
+    }
+    const std::string tmp = std::string(path) + ".tmp." + std::to_string((long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(e, CLK_EIO, "open %s: %s", tmp.c_str(), strerror(errno));
+    const bool wrote = fwrite(w.b.data(), 1, w.b.size(), f) == w.b.size();
+    const bool closed = fclose(f) == 0;
+    if (!wrote || !closed || rename(tmp.c_str(), path) != 0) { int en = errno; remove(tmp.c_str()); return fail(e, CLK_EIO, "write %s: %s", path, strerror(en)); }
+    return CLK_OK;
+}
+
+int clk_state_load(clk_engine *e, const char *path)
+{
+    if (!e || !path || !*path) return fail(e, CLK_EINVAL, "NULL");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(e, errno == ENOENT ? CLK_ENOENT : CLK_EIO, "open %s: %s", path, strerror(errno));
+    std::string buf; char chunk[1 << 16]; size_t k;
+    while ((k = fread(chunk, 1, sizeof chunk, f)) > 0) buf.append(chunk, k);
+    fclose(f);
+    PinReader r(buf);
+    char magic[8]; r.raw(magic, 8);
+    if (!r.ok || memcmp(magic, kPinMagic, 8) != 0) return fail(e, CLK_EINVAL, "%s is not a clawker-gpu state file (or a different version)", path);
+    // parse into fresh tables first: a truncated or oversized file must leave the engine untouched
+    decltype(e->container) container; decltype(e->bypass) bypass; decltype(e->dns) dns; decltype(e->route) route;
+    decltype(e->endpoint) endpoint; decltype(e->endpoint6) endpoint6; decltype(e->cidr) cidr; CompiledRules comp;
+    for (;;) {
+        const uint32_t tag = r.u32(); const uint64_t n = r.u64();
+        if (!r.ok) return fail(e, CLK_EINVAL, "%s: truncated", path);
+        if (tag == PIN_END) break;
+        if (n > (buf.size() - r.p)) return fail(e, CLK_EINVAL, "%s: section %u claims %llu rows", path, tag, (unsigned long long)n);
+        for (uint64_t i = 0; i < n && r.ok; i++) {
+            switch (tag) {
+            case PIN_CONTAINER: { uint64_t cg = r.u64(); clk_container_config c; r.raw(&c, sizeof c); container[cg] = c; break; }
+            case PIN_BYPASS:    { uint64_t cg = r.u64(); uint8_t v; r.raw(&v, 1); bypass[cg] = v; break; }
+            case PIN_DNS:       { uint32_t ip = r.u32(); clk_dns_entry d; r.raw(&d, sizeof d); dns[ip] = d; break; }
+            case PIN_ROUTE:     { uint64_t rk = r.u64(); uint16_t v; r.raw(&v, 2); route[rk] = v; break; }
+            case PIN_EP:        { uint32_t ip = r.u32(); clk_endpoint ep; r.raw(&ep, sizeof ep); endpoint[ip] = ep; break; }
+            case PIN_EP6:       { std::array<uint8_t, 16> a; r.raw(a.data(), 16); clk_endpoint ep; r.raw(&ep, sizeof ep); endpoint6[a] = ep; break; }
+            case PIN_CIDR:      { uint32_t a = r.u32(), m = r.u32(); if (!is_cidr_mask(m)) return fail(e, CLK_EINVAL, "%s: mask %#x is not a CIDR prefix mask", path, m); cidr[{ a, m }] = 1; break; }
+            case PIN_ZONES:     comp.zones.push_back(r.str()); break;
+            case PIN_SNIS:      comp.snis.push_back(r.str()); break;
+            case PIN_MAPPINGS:  { TCPMapping m; m.dst = r.str(); m.dst_port = (int)r.u32(); m.envoy_port = (int)r.u32(); comp.mappings.push_back(m); break; }
+            case PIN_CCIDRS:    { uint32_t a = r.u32(), m = r.u32(); comp.cidrs.push_back({ a, m }); break; }
+            default: return fail(e, CLK_EINVAL, "%s: unknown section %u", path, tag);
+            }
+        }
+        if (!r.ok) return fail(e, CLK_EINVAL, "%s: truncated", path);
+    }
+    std::lock_guard<std::mutex> g(e->mu);
+    if (container.size() > e->max_containers || bypass.size() > e->max_containers) return fail(e, CLK_E2BIG, "%s: %zu containers > max_entries %u", path, container.size(), e->max_containers);
+    if (dns.size() > e->max_dns) return fail(e, CLK_E2BIG, "%s: %zu dns_cache rows > max_entries %u", path, dns.size(), e->max_dns);
+    if (route.size() > e->max_routes) return fail(e, CLK_E2BIG, "%s: %zu routes > max_entries %u", path, route.size(), e->max_routes);
+    if (cidr.size() > e->max_cidrs) return fail(e, CLK_E2BIG, "%s: %zu CIDRs > %u", path, cidr.size(), e->max_cidrs);
+    if (endpoint6.size() > 256) return fail(e, CLK_E2BIG, "%s: %zu IPv6 endpoints > 256", path, endpoint6.size());
+    e->container.swap(container); e->bypass.swap(bypass); e->dns.swap(dns); e->route.swap(route);
+    e->endpoint.swap(endpoint); e->endpoint6.swap(endpoint6); e->cidr.swap(cidr); e->compiled = std::move(comp);
+    e->dirty = true;
     return CLK_OK;
 }
 

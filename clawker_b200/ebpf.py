@@ -63,12 +63,15 @@ class Manager:
     def __init__(self, engine: Engine | None = None, **engine_kw):
         self.e = engine if engine is not None else Engine(**engine_kw)
 
-    # Load / OpenPinned (manager.go:41-133): the engine already holds the (empty) maps.
-    def Load(self):
-        return None
+    # Load / OpenPinned (manager.go:41-133): the engine already holds the (empty) maps; with a pin path they are
+    # shared with the `ebpf-manager` verbs through the state file (the bpffs analogue, clk_state_save / _load).
+    def Load(self, pin_path: str | None = None):
+        if pin_path:
+            self.e.state_save(pin_path)
 
-    def OpenPinned(self):
-        return None
+    def OpenPinned(self, pin_path: str | None = None):
+        if pin_path:
+            self.e.state_load(pin_path)
 
     def Close(self):
         self.e.close()

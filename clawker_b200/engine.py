@@ -19,6 +19,7 @@ from .abi import (Cfg, ContainerConfig, DNSEntry, Endpoint, Cidr, Ports, Route, 
 
 PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["CLK_LIB"]) if os.environ.get("CLK_LIB") else PKG / "libclawker_gpu.so"
+CLI_PATH = PKG / "ebpf-manager"                   # control-plane verbs on the pinned state (csrc/ebpf_manager.cpp)
 
 
 class ClkError(RuntimeError):
@@ -30,7 +31,7 @@ class ClkError(RuntimeError):
 def build_library(force: bool = False) -> Path:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> clawker_b200/libclawker_gpu.so (in-tree)."""
     srcs = list((PKG / "csrc").glob("*")) + [PKG.parent / "include" / "clawker_gpu.h"]
-    stale = not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs)
+    stale = not LIB_PATH.exists() or not CLI_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs)
     if force or stale:
         r = subprocess.run(["make", "-C", str(PKG / "csrc")] + (["-B"] if force else []), capture_output=True, text=True)
         if r.returncode != 0:
@@ -83,6 +84,8 @@ def lib() -> C.CDLL:
         "clk_counters_block_rows": (i32, [vp, C.POINTER(u32)]),
         "clk_counters_export": (i32, [vp, vp, vp]),
         "clk_counters_import": (i32, [vp, vp, u32, vp]),
+        "clk_state_save": (i32, [vp, C.c_char_p]),
+        "clk_state_load": (i32, [vp, C.c_char_p]),
         "clk_totals_rows": (i32, [vp, C.POINTER(u32)]),
         "clk_totals_export": (i32, [vp, vp, vp]),
         "clk_totals_merge": (i32, [vp, vp, u32, vp, u32, C.POINTER(u32)]),
@@ -104,7 +107,7 @@ EXPORTS = ["clk_abi_version", "clk_strerror", "clk_last_error", "clk_engine_crea
            "clk_cidr_to_addr_mask", "clk_rules_compile", "clk_rules_dump", "clk_publish", "clk_classify_slots",
            "clk_classify_varlen", "clk_classify_slots_dev", "clk_classify_varlen_dev", "clk_classify_events",
            "clk_dns_answers", "clk_counters_read", "clk_counters_read_global", "clk_counters_reset", "clk_counters_block_rows",
-           "clk_counters_export", "clk_counters_import", "clk_totals_rows", "clk_totals_export", "clk_totals_merge", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
+           "clk_counters_export", "clk_counters_import", "clk_totals_rows", "clk_totals_export", "clk_totals_merge", "clk_state_save", "clk_state_load", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
 
 
 def pinned_empty(nbytes: int) -> np.ndarray:
@@ -180,6 +183,23 @@ class Engine:
         n = C.c_uint32()
         self._ck(self.L.clk_map_count(self.h, map_id, C.byref(n)))
         return n.value
+
+    _MAP_SIZES = {0: (8, 28), 1: (8, 1), 2: (4, 8), 3: (8, 4), 5: (4, 16), 6: (16, 16), 7: (8, 1)}
+
+    def map_rows(self, map_id: int) -> dict:
+        """Every row of a map as {key bytes: value bytes} (clk_map_iter)."""
+        klen, vlen = self._MAP_SIZES[map_id]
+        n = self.map_count(map_id)
+        keys, vals, got = C.create_string_buffer(max(1, n * klen)), C.create_string_buffer(max(1, n * vlen)), C.c_uint32()
+        self._ck(self.L.clk_map_iter(self.h, map_id, keys, vals, n, C.byref(got)))
+        return {keys.raw[i * klen:(i + 1) * klen]: vals.raw[i * vlen:(i + 1) * vlen] for i in range(min(n, got.value))}
+
+    # the pinned state shared with the `ebpf-manager` verbs (SURVEY 8(f) F2)
+    def state_save(self, path: str):
+        self._ck(self.L.clk_state_save(self.h, os.fsencode(path)))
+
+    def state_load(self, path: str):
+        self._ck(self.L.clk_state_load(self.h, os.fsencode(path)))
 
     def routes_replace(self, routes):
         arr = (Route * len(routes))(*[Route(*r) for r in routes])

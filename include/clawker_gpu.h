@@ -365,6 +365,16 @@ int clk_get_stats(clk_engine *e, clk_stats *out);
 /* Block until the engine stream is idle. */
 int clk_sync(clk_engine *e);
 
+/* ---- pinned state ------------------------------------------- */
+/* The reference keeps its maps pinned in bpffs (/sys/fs/bpf/clawker, manager.go:27-38,111-133) so that
+ * each `ebpf-manager <verb>` process can open, change and leave them (cmd/main.go:84-143).  The GPU
+ * engine's analogue is a state file: clk_state_save writes every table (container, bypass, dns_cache,
+ * route, endpoint, endpoint6, cidr and the compiled zone / server_names / TCP-mapping sets) atomically
+ * (temp file + rename); clk_state_load replaces the engine's tables with the file's (the next classify
+ * call publishes them).  Both work on host-only engines — the control-plane binary needs no GPU. */
+int clk_state_save(clk_engine *e, const char *path);
+int clk_state_load(clk_engine *e, const char *path);
+
 /* Pinned (page-locked) host memory for ingest rings: buffers from here are DMA'd directly by the
  * host-buffer entry points; ordinary pageable memory also works, through the driver's staging. */
 int clk_host_alloc(size_t bytes, void **out);

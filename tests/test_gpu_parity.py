@@ -73,6 +73,22 @@ def test_metrics_map_full_is_strict():
     assert int(rows[0]["count"]) == got.size
 
 
+def test_state_file_drives_the_gpu_engine(tmp_path):
+    """The pinned state written by the control plane (`ebpf-manager` verbs, clk_state_save) is all a classifying
+    process needs: load, publish, same verdicts as the engine that was configured call by call."""
+    from clawker_b200 import engine
+    w = capture.make_workload("c2")
+    pk = capture.gen_slots(w, 120_000, seed=31, v6_frac=0.02)
+    want, wm = oracle.Oracle("port").load(oracle_tables(w)).classify(pk)
+    e1 = make_engine(w)
+    p = str(tmp_path / "maps.pin")
+    e1.state_save(p)
+    e2 = engine.Engine(max_metrics=1 << 20, max_dns_cache=1 << 21, max_routes=1 << 16, max_containers=4096)
+    e2.state_load(p)
+    assert_same_verdicts(e2.classify_slots(pk), want, "engine loaded from the state file")
+    assert_same_metrics(e2.counters(), wm, "engine loaded from the state file")
+
+
 def test_c2_vs_reference_object():
     """No CIDR rules -> the decision stage must equal the reference's own eBPF C."""
     if not oracle.have_ref():
