@@ -84,6 +84,9 @@ def lib() -> C.CDLL:
         "clk_counters_block_rows": (i32, [vp, C.POINTER(u32)]),
         "clk_counters_export": (i32, [vp, vp, vp]),
         "clk_counters_import": (i32, [vp, vp, u32, vp]),
+        "clk_pcap_pack": (i32, [C.c_char_p, C.POINTER(u64), vp, u64, vp, u64, C.POINTER(u64)]),
+        "clk_classify_pcap": (i32, [vp, C.c_char_p, u32, vp, u64, C.POINTER(u64)]),
+        "clk_pcap_last_error": (C.c_char_p, []),
         "clk_state_save": (i32, [vp, C.c_char_p]),
         "clk_state_load": (i32, [vp, C.c_char_p]),
         "clk_totals_rows": (i32, [vp, C.POINTER(u32)]),
@@ -107,7 +110,24 @@ EXPORTS = ["clk_abi_version", "clk_strerror", "clk_last_error", "clk_engine_crea
            "clk_cidr_to_addr_mask", "clk_rules_compile", "clk_rules_dump", "clk_publish", "clk_classify_slots",
            "clk_classify_varlen", "clk_classify_slots_dev", "clk_classify_varlen_dev", "clk_classify_events",
            "clk_dns_answers", "clk_counters_read", "clk_counters_read_global", "clk_counters_reset", "clk_counters_block_rows",
-           "clk_counters_export", "clk_counters_import", "clk_totals_rows", "clk_totals_export", "clk_totals_merge", "clk_state_save", "clk_state_load", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
+           "clk_counters_export", "clk_counters_import", "clk_totals_rows", "clk_totals_export", "clk_totals_merge", "clk_state_save", "clk_state_load", "clk_pcap_pack", "clk_classify_pcap", "clk_pcap_last_error", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
+
+
+def pcap_pack(path: str, cap_bytes: int = 64 << 20, cap_frames: int = 1 << 20):
+    """Generator over a classic pcap file: (blob, offs16) chunks in the varlen layout (clk_pcap_pack)."""
+    L = lib()
+    cursor = C.c_uint64(0)
+    while True:
+        blob, offs, n = np.zeros(cap_bytes, dtype=np.uint8), np.zeros(cap_frames + 1, dtype=np.uint32), C.c_uint64()
+        rc = L.clk_pcap_pack(os.fsencode(path), C.byref(cursor), blob.ctypes.data, cap_bytes, offs.ctypes.data, cap_frames, C.byref(n))
+        if rc:
+            raise ClkError(rc, L.clk_pcap_last_error().decode())
+        if n.value:
+            yield blob[: int(offs[n.value]) * 16], offs[: n.value + 1]
+        elif cursor.value:
+            raise ClkError(-7, "a frame does not fit the chunk buffers")
+        if cursor.value == 0:
+            return
 
 
 def pinned_empty(nbytes: int) -> np.ndarray:
@@ -193,6 +213,20 @@ class Engine:
         keys, vals, got = C.create_string_buffer(max(1, n * klen)), C.create_string_buffer(max(1, n * vlen)), C.c_uint32()
         self._ck(self.L.clk_map_iter(self.h, map_id, keys, vals, n, C.byref(got)))
         return {keys.raw[i * klen:(i + 1) * klen]: vals.raw[i * vlen:(i + 1) * vlen] for i in range(min(n, got.value))}
+
+    # capture files
+    def classify_pcap(self, path: str, flags: int = 0) -> np.ndarray:
+        """Verdict word per frame of a classic pcap file (read, packed and classified in overlapped chunks)."""
+        n = C.c_uint64()
+        rc = self.L.clk_classify_pcap(self.h, os.fsencode(path), flags, None, 0, C.byref(n))      # count first
+        if rc:
+            raise ClkError(rc, self.L.clk_pcap_last_error().decode())
+        out = np.empty(n.value, dtype=np.uint32)
+        if n.value:
+            rc = self.L.clk_classify_pcap(self.h, os.fsencode(path), flags, out.ctypes.data, n.value, C.byref(n))
+            if rc:
+                raise ClkError(rc, self.L.clk_pcap_last_error().decode())
+        return out
 
     # the pinned state shared with the `ebpf-manager` verbs (SURVEY 8(f) F2)
     def state_save(self, path: str):

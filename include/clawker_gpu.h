@@ -365,6 +365,20 @@ int clk_get_stats(clk_engine *e, clk_stats *out);
 /* Block until the engine stream is idle. */
 int clk_sync(clk_engine *e);
 
+/* ---- capture-file ingest ------------------------------------ */
+/* Classic pcap (magic a1b2c3d4 or a1b23c4d, either byte order, LINKTYPE_ETHERNET) -> the varlen
+ * layout of clk_classify_varlen.  clk_pcap_pack fills caller buffers from file offset *cursor
+ * (0 = first record) until a capacity runs out, sets *cursor to the next unread record (0 once the
+ * file is exhausted; a truncated last record ends the file) and offs16[0..n_frames].
+ * clk_classify_pcap runs a whole file: chunks are read and packed into pinned double buffers on a
+ * helper thread while the previous chunk is in the H2D / kernel / D2H pipeline; *n = frames in the
+ * file, verdicts receives the first min(*n, cap).  Errors from these two: clk_pcap_last_error(). */
+int clk_pcap_pack(const char *path, uint64_t *cursor, uint8_t *blob, uint64_t cap_bytes,
+                  uint32_t *offs16, uint64_t cap_frames, uint64_t *n_frames);
+int clk_classify_pcap(clk_engine *e, const char *path, uint32_t flags, uint32_t *verdicts,
+                      uint64_t cap, uint64_t *n);
+const char *clk_pcap_last_error(void);
+
 /* ---- pinned state ------------------------------------------- */
 /* The reference keeps its maps pinned in bpffs (/sys/fs/bpf/clawker, manager.go:27-38,111-133) so that
  * each `ebpf-manager <verb>` process can open, change and leave them (cmd/main.go:84-143).  The GPU
