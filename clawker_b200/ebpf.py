@@ -111,6 +111,10 @@ class Manager:
             raise KeyNotExist(cgroup_id)
         return v
 
+    def ScrapeMetrics(self, merged: bool = False):
+        """The reader the reference planned (outstanding-features.md:262-300): the metrics_map rows (see exporter.py)."""
+        return self.e.counters(merged=merged)
+
     # ---- extension: the packet -> socket identity binding (SURVEY §8(d)) -----------------------------
     def BindEndpoint(self, ip: str, cgroup_id: int, uid: int = 1000, so_mark: int = 0):
         self.e.map_update(abi.MAP_ENDPOINT, C.c_uint32(IPToUint32(ip)), Endpoint(cgroup_id, uid, so_mark))
