@@ -47,8 +47,13 @@ class Cfg(C.Structure):
                 ("max_cidrs", C.c_uint32), ("flags", C.c_uint32), ("reserved_sms", C.c_uint32)]
 
 
-class Rule(C.Structure):
-    _fields_ = [("dst", C.c_char_p), ("proto", C.c_char_p), ("port", C.c_int32), ("action", C.c_char_p)]
+class PathRule(C.Structure):                   # config.PathRule schema.go:124-127
+    _fields_ = [("path", C.c_char_p), ("action", C.c_char_p)]
+
+
+class Rule(C.Structure):                       # config.EgressRule schema.go:131-138
+    _fields_ = [("dst", C.c_char_p), ("proto", C.c_char_p), ("port", C.c_int32), ("action", C.c_char_p),
+                ("path_default", C.c_char_p), ("path_rules", C.POINTER(PathRule)), ("n_path_rules", C.c_uint32)]
 
 
 class Ports(C.Structure):

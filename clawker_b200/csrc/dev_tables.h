@@ -82,6 +82,8 @@ struct NameSlot {
     uint32_t str_off;           // offset into names blob: [len u8][bytes]
 };
 
+enum { HTTP_K_EXACT = 0, HTTP_K_SUFFIX = 1, HTTP_K_PREFIX = 2 };
+
 // ---- dns_cache / route_map: 2-choice bucketed tables -------------------------------------------
 // A bucket is one 16-byte word holding two 8-byte slots, so a lookup is one 128-bit load and a
 // miss is decided without a probe loop: keys go to bucket b1 while it has room, else to b2.
@@ -128,6 +130,11 @@ struct DevTables {
     const uint32_t *cidr_l2_keys; const uint32_t *cidr_l2_bits; uint32_t cidr_l2_mask, cidr_l2_shift;   // key: block+1; bits: 8 words / slot
     const NameSlot *zone_slots;  uint32_t zone_mask;
     const NameSlot *sni_slots;   uint32_t sni_mask;
+    // F3: plaintext HTTP virtual hosts.  Table strings: exact "d" | suffix ".d" (of "*.d") | prefix "d:" (of "d:*");
+    // val = virtual-host index | kind << 28.  http_vh[v] = names-blob offset of the route list
+    // [n u8] n x { allow u8, len u8, prefix bytes }.
+    const NameSlot *http_slots;  uint32_t http_mask;
+    const uint32_t *http_vh;     uint32_t n_http;
     const uint8_t  *names;                               // blob for string confirmation
     uint32_t coredns_ips[8];     uint32_t n_coredns;     // distinct cfg.coredns_ip values (DNS-answer stage)
     // device metrics table

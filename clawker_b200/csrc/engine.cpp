@@ -17,6 +17,7 @@
 #include <ctime>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -50,8 +51,8 @@ struct DevBuf {
 };
 
 struct Snapshot {
-    DevBuf ep_rows, ep_slots, ep_soa, ep6, crows, cg_slots, dns, route, cidr_pre, cidr_l1, cidr_l2_keys, cidr_l2_bits, zone, sni, names;
-    void release() { for (DevBuf *b : { &ep_rows, &ep_slots, &ep_soa, &ep6, &crows, &cg_slots, &dns, &route, &cidr_pre, &cidr_l1, &cidr_l2_keys, &cidr_l2_bits, &zone, &sni, &names }) b->release(); }
+    DevBuf ep_rows, ep_slots, ep_soa, ep6, crows, cg_slots, dns, route, cidr_pre, cidr_l1, cidr_l2_keys, cidr_l2_bits, zone, sni, names, http, http_vh;
+    void release() { for (DevBuf *b : { &ep_rows, &ep_slots, &ep_soa, &ep6, &crows, &cg_slots, &dns, &route, &cidr_pre, &cidr_l1, &cidr_l2_keys, &cidr_l2_bits, &zone, &sni, &names, &http, &http_vh }) b->release(); }
 };
 
 struct MetricKeyHash {
@@ -134,6 +135,8 @@ bool is_cidr_mask(uint32_t mask_nbo)
     return ((~h) & ((~h) + 1)) == 0;          // ~h is 2^k - 1
 }
 int mask_plen(uint32_t mask_nbo) { return __builtin_popcount(mask_nbo); }
+
+std::string to_lower_ascii(std::string s) { for (auto &c : s) if (c >= 'A' && c <= 'Z') c = (char)(c + 32); return s; }
 
 uint64_t name_key_of(const std::string &s)
 {
@@ -336,6 +339,35 @@ int publish_locked(clk_engine *e)
         std::vector<uint32_t> vals(e->compiled.snis.size()); for (size_t i = 0; i < vals.size(); i++) vals[i] = (uint32_t)i;
         build_name_table(e->compiled.snis, vals, sni_slots, blob);
     }
+    // F3: virtual hosts of the plaintext-HTTP chain.  Domain forms (envoy.go:932-944): "d" exact, "*.d" suffix
+    // wildcard (stored ".d"), "d:*" prefix wildcard (stored "d:"); the first virtual host that lists a form owns it.
+    std::vector<NameSlot> http_slots; std::vector<uint32_t> http_vh;
+    if (!e->compiled.http.empty()) {
+        std::vector<std::string> names; std::vector<uint32_t> vals; std::set<std::pair<uint32_t, std::string>> seen;
+        for (size_t v = 0; v < e->compiled.http.size(); v++) {
+            for (const std::string &d : e->compiled.http[v].domains) {
+                if (d == "*" || d.empty()) continue;                    // the catch-all is the implicit deny_all host
+                uint32_t kind; std::string str;
+                if (d[0] == '*') { kind = HTTP_K_SUFFIX; str = d.substr(1); }
+                else if (d.back() == '*') { kind = HTTP_K_PREFIX; str = d.substr(0, d.size() - 1); }
+                else { kind = HTTP_K_EXACT; str = d; }
+                if (str.size() > 255 || (kind == HTTP_K_SUFFIX && str[0] != '.') || (kind == HTTP_K_PREFIX && str.back() != ':'))
+                    return fail(e, CLK_EINVAL, "virtual-host domain \"%s\": unsupported form", d.c_str());
+                if (!seen.insert({ kind, to_lower_ascii(str) }).second) continue;
+                names.push_back(str); vals.push_back((uint32_t)v | (kind << 28));
+            }
+            const auto &routes = e->compiled.http[v].routes;
+            if (routes.size() > 255) return fail(e, CLK_E2BIG, "virtual host %zu: %zu routes > 255", v, routes.size());
+            http_vh.push_back((uint32_t)blob.size());
+            blob.push_back((uint8_t)routes.size());
+            for (const auto &r : routes) {
+                if (r.prefix.size() > 255) return fail(e, CLK_E2BIG, "path prefix longer than 255 bytes");
+                blob.push_back(r.allow ? 1 : 0); blob.push_back((uint8_t)r.prefix.size());
+                blob.insert(blob.end(), r.prefix.begin(), r.prefix.end());
+            }
+        }
+        build_name_table(names, vals, http_slots, blob);
+    }
     // ---- upload -------------------------------------------------------------------------------------
     CUDA_TRY(e, upload(S.crows, crows, st));       CUDA_TRY(e, upload(S.cg_slots, cg_slots, st));
     // the fields the fast path needs, packed as three 16-byte words per row (48 B stride: conflict-free LDS.128 for 8 rows)
@@ -354,6 +386,7 @@ int publish_locked(clk_engine *e)
     CUDA_TRY(e, upload(S.cidr_l2_bits, l2_bits, st));
     CUDA_TRY(e, upload(S.zone, zone_slots, st));   CUDA_TRY(e, upload(S.sni, sni_slots, st));
     CUDA_TRY(e, upload(S.names, blob, st));
+    CUDA_TRY(e, upload(S.http, http_slots, st));   CUDA_TRY(e, upload(S.http_vh, http_vh, st));
     CUDA_TRY(e, cudaStreamSynchronize(st));
 
     T.ep_rows = rows.empty() ? nullptr : (const EpRow *)S.ep_rows.p; T.n_ep_rows = (uint32_t)rows.size();
@@ -370,6 +403,10 @@ int publish_locked(clk_engine *e)
     if (!zone_slots.empty()) { T.zone_slots = (const NameSlot *)S.zone.p; T.zone_mask = (uint32_t)zone_slots.size() - 1; }
     if (!sni_slots.empty()) { T.sni_slots = (const NameSlot *)S.sni.p; T.sni_mask = (uint32_t)sni_slots.size() - 1; }
     T.names = (const uint8_t *)S.names.p;
+    if (!http_vh.empty()) {
+        T.n_http = (uint32_t)http_vh.size(); T.http_vh = (const uint32_t *)S.http_vh.p;
+        if (!http_slots.empty()) { T.http_slots = (const NameSlot *)S.http.p; T.http_mask = (uint32_t)http_slots.size() - 1; }
+    }
     // distinct CoreDNS addresses (DNS-answer stage)
     for (auto &kv : e->container) {
         bool seen = false;
@@ -634,6 +671,10 @@ int clk_rules_compile(clk_engine *e, const clk_rule *rules, uint32_t n, const cl
     for (uint32_t i = 0; i < n; i++) {
         rs[i].dst = rules[i].dst ? rules[i].dst : ""; rs[i].proto = rules[i].proto ? rules[i].proto : "";
         rs[i].action = rules[i].action ? rules[i].action : ""; rs[i].port = rules[i].port;
+        rs[i].path_default = rules[i].path_default ? rules[i].path_default : "";
+        if (rules[i].n_path_rules && !rules[i].path_rules) return fail(e, CLK_EINVAL, "rule %u: path_rules is NULL", i);
+        for (uint32_t k = 0; k < rules[i].n_path_rules; k++)
+            rs[i].path_rules.push_back({ rules[i].path_rules[k].path ? rules[i].path_rules[k].path : "", rules[i].path_rules[k].action ? rules[i].path_rules[k].action : "" });
     }
     int base = ports && ports->tcp_port_base ? ports->tcp_port_base : 10001;
     CompiledRules c = compile_rules(rs, base);
@@ -658,6 +699,12 @@ int clk_rules_dump(clk_engine *e, int kind, char *buf, size_t cap)
     if (kind == 0) for (auto &z : e->compiled.zones) s += z + "\n";
     else if (kind == 1) for (auto &z : e->compiled.snis) s += z + "\n";
     else if (kind == 2) for (auto &m : e->compiled.mappings) s += m.dst + ":" + std::to_string(m.dst_port) + ":" + std::to_string(m.envoy_port) + "\n";
+    else if (kind == 3) for (auto &v : e->compiled.http) {               // one virtual host per line: domains | routes (A = allow, D = deny)
+        for (size_t i = 0; i < v.domains.size(); i++) s += (i ? "," : "") + v.domains[i];
+        s += "|";
+        for (size_t i = 0; i < v.routes.size(); i++) s += std::string(i ? "," : "") + (v.routes[i].allow ? "A" : "D") + v.routes[i].prefix;
+        s += "\n";
+    }
     else return fail(e, CLK_EINVAL, "kind %d", kind);
     if (buf && cap) { size_t k = std::min(cap - 1, s.size()); memcpy(buf, s.data(), k); buf[k] = 0; }
     return (int)s.size() + 1;
@@ -974,7 +1021,7 @@ struct PinReader {
     uint64_t u64() { uint64_t v; raw(&v, 8); return v; }
     std::string str() { uint32_t n = u32(); if (!ok || p + n > b.size()) { ok = false; return ""; } std::string s(b.data() + p, n); p += n; return s; }
 };
-enum { PIN_END = 0, PIN_CONTAINER, PIN_BYPASS, PIN_DNS, PIN_ROUTE, PIN_EP, PIN_EP6, PIN_CIDR, PIN_ZONES, PIN_SNIS, PIN_MAPPINGS, PIN_CCIDRS };
+enum { PIN_END = 0, PIN_CONTAINER, PIN_BYPASS, PIN_DNS, PIN_ROUTE, PIN_EP, PIN_EP6, PIN_CIDR, PIN_ZONES, PIN_SNIS, PIN_MAPPINGS, PIN_CCIDRS, PIN_HTTP };
 }  // namespace
 
 int clk_state_save(clk_engine *e, const char *path)
@@ -995,6 +1042,11 @@ int clk_state_save(clk_engine *e, const char *path)
         w.section(PIN_SNIS, e->compiled.snis.size());   for (auto &z : e->compiled.snis) w.str(z);
         w.section(PIN_MAPPINGS, e->compiled.mappings.size()); for (auto &m : e->compiled.mappings) { w.str(m.dst); w.u32((uint32_t)m.dst_port); w.u32((uint32_t)m.envoy_port); }
         w.section(PIN_CCIDRS, e->compiled.cidrs.size()); for (auto &c : e->compiled.cidrs) { w.u32(c.first); w.u32(c.second); }
+        w.section(PIN_HTTP, e->compiled.http.size());
+        for (auto &v : e->compiled.http) {
+            w.u32((uint32_t)v.domains.size()); for (auto &d : v.domains) w.str(d);
+            w.u32((uint32_t)v.routes.size());  for (auto &r : v.routes) { w.u32(r.allow ? 1u : 0u); w.str(r.prefix); }
+        }
         w.section(PIN_END, 0);
     }
     const std::string tmp = std::string(path) + ".tmp." + std::to_string((long)getpid());
@@ -1038,6 +1090,13 @@ int clk_state_load(clk_engine *e, const char *path)
             case PIN_SNIS:      comp.snis.push_back(r.str()); break;
             case PIN_MAPPINGS:  { TCPMapping m; m.dst = r.str(); m.dst_port = (int)r.u32(); m.envoy_port = (int)r.u32(); comp.mappings.push_back(m); break; }
             case PIN_CCIDRS:    { uint32_t a = r.u32(), m = r.u32(); comp.cidrs.push_back({ a, m }); break; }
+            case PIN_HTTP: {
+                HttpVhost v; uint32_t nd = r.u32();
+                for (uint32_t k = 0; k < nd && r.ok; k++) v.domains.push_back(r.str());
+                uint32_t nr = r.u32();
+                for (uint32_t k = 0; k < nr && r.ok; k++) { HttpRoute hr; hr.allow = r.u32() != 0; hr.prefix = r.str(); v.routes.push_back(hr); }
+                comp.http.push_back(std::move(v)); break;
+            }
             default: return fail(e, CLK_EINVAL, "%s: unknown section %u", path, tag);
             }
         }

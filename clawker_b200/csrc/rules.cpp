@@ -210,6 +210,28 @@ CompiledRules compile_rules(const std::vector<EgressRule> &in, int tcp_port_base
             for (auto &s : names) if (have.insert(s).second) out.snis.push_back(s);
         }
     }
+    // raw_buffer (plaintext HTTP) chain: httpRules envoy.go:197-203, httpExactDomains :222-227,
+    // httpDomains :932-944, routes :411-425 + buildHTTPRoutes :566-607
+    {
+        std::vector<const EgressRule *> hs;
+        for (const auto &r : rules) if (is_allow(r) && !is_ip_or_cidr(r.dst) && to_lower(r.proto) == "http") hs.push_back(&r);
+        std::unordered_set<std::string> exact;
+        for (auto r : hs) if (!is_wildcard_domain(r->dst)) exact.insert(normalize_domain(r->dst));
+        for (auto r : hs) {
+            HttpVhost v; const std::string d = normalize_domain(r->dst);
+            if (is_wildcard_domain(r->dst)) {
+                v.domains = { "*." + d, "*." + d + ":*" };
+                if (!exact.count(d)) { v.domains.push_back(d); v.domains.push_back(d + ":*"); }
+            } else v.domains = { d, d + ":*" };
+            if (r->path_rules.empty()) v.routes.push_back({ "/", true });
+            else {
+                for (auto &pr : r->path_rules) v.routes.push_back({ pr.first, to_lower(pr.second) == "allow" });
+                const std::string pd = to_lower(r->path_default);
+                v.routes.push_back({ "/", !(pd.empty() || pd == "deny") });
+            }
+            out.http.push_back(std::move(v));
+        }
+    }
     // TCPMappings, envoy.go:54-83
     {
         int idx = 0;

@@ -7,10 +7,15 @@
 
 namespace clk {
 
-struct EgressRule {            // config.EgressRule, internal/config/schema.go:131-138
+struct EgressRule {            // config.EgressRule, internal/config/schema.go:124-138
     std::string dst, proto, action;
     int port = 0;
+    std::vector<std::pair<std::string, std::string>> path_rules;   // PathRule {path, action}
+    std::string path_default;
 };
+
+struct HttpRoute { std::string prefix; bool allow; };                      // buildHTTPRoutes envoy.go:566-607
+struct HttpVhost { std::vector<std::string> domains; std::vector<HttpRoute> routes; };   // buildHTTPFilterChain envoy.go:403-425
 
 struct TCPMapping { std::string dst; int dst_port; int envoy_port; };     // firewall.TCPMapping envoy.go:46-50
 
@@ -19,6 +24,7 @@ struct CompiledRules {
     std::vector<std::string> snis;         // filter_chain_match.server_names in chain order (envoy.go:358-393,905-915)
     std::vector<TCPMapping>  mappings;     // TCPMappings (envoy.go:54-83)
     std::vector<std::pair<uint32_t, uint32_t>> cidrs;   // A12: (addr, mask), NBO-in-native
+    std::vector<HttpVhost>   http;         // F3: http_egress_routes virtual hosts in config order (deny_all "*" is implicit)
     uint32_t warnings = 0;                 // rules skipped by normalizeAndDedup (rules.go:146-150)
 };
 

@@ -274,9 +274,13 @@ class Engine:
         arr = (Rule * len(rules))()
         keep = []
         for i, r in enumerate(rules):
-            b = [str(g(r, "dst", "")).encode(), str(g(r, "proto", "") or "").encode(), str(g(r, "action", "") or "").encode()]
-            keep.append(b)
-            arr[i] = Rule(b[0], b[1], int(g(r, "port", 0) or 0), b[2])
+            b = [str(g(r, "dst", "")).encode(), str(g(r, "proto", "") or "").encode(), str(g(r, "action", "") or "").encode(),
+                 str(g(r, "path_default", "") or "").encode()]
+            prs = [((x["path"], x.get("action", "")) if isinstance(x, dict) else (x[0], x[1])) for x in (g(r, "path_rules", None) or [])]
+            pb = [(str(p).encode(), str(a or "").encode()) for p, a in prs]
+            parr = (abi.PathRule * len(pb))(*[abi.PathRule(p, a) for p, a in pb]) if pb else None
+            keep.append((b, pb, parr))
+            arr[i] = Rule(b[0], b[1], int(g(r, "port", 0) or 0), b[2], b[3], parr, len(pb))
         w = C.c_uint32()
         ports = Ports(egress_port, tcp_port_base)
         self._ck(self.L.clk_rules_compile(self.h, arr, len(rules), C.byref(ports), C.byref(w)))

@@ -130,9 +130,13 @@ func (e *Engine) DNSGC(now uint32) (int, error) {
 }
 
 // Rule is config.EgressRule restricted to the fields on this path.
+type PathRule struct{ Path, Action string }
+
 type Rule struct {
 	Dst, Proto, Action string
 	Port               int
+	PathRules          []PathRule // proto http: Host + path-prefix stage
+	PathDefault        string
 }
 
 // RulesCompile replaces the zone table, the SNI table, the CIDR set and route_map from rules.
@@ -146,7 +150,15 @@ func (e *Engine) RulesCompile(rules []Rule, egressPort, tcpPortBase int) (warnin
 	}()
 	cs := func(s string) *C.char { p := C.CString(s); frees = append(frees, unsafe.Pointer(p)); return p }
 	for i, r := range rules {
-		cr[i] = C.clk_rule{dst: cs(r.Dst), proto: cs(r.Proto), port: C.int32_t(r.Port), action: cs(r.Action)}
+		cr[i] = C.clk_rule{dst: cs(r.Dst), proto: cs(r.Proto), port: C.int32_t(r.Port), action: cs(r.Action), path_default: cs(r.PathDefault)}
+		if n := len(r.PathRules); n > 0 { // the array lives in C memory: cgo forbids Go pointers to Go pointers
+			arr := (*C.clk_path_rule)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof(C.clk_path_rule{}))))
+			frees = append(frees, unsafe.Pointer(arr))
+			for k, pr := range r.PathRules {
+				(*[1 << 20]C.clk_path_rule)(unsafe.Pointer(arr))[k] = C.clk_path_rule{path: cs(pr.Path), action: cs(pr.Action)}
+			}
+			cr[i].path_rules, cr[i].n_path_rules = arr, C.uint32_t(n)
+		}
 	}
 	ports := C.clk_ports{egress_port: C.int32_t(egressPort), tcp_port_base: C.int32_t(tcpPortBase)}
 	var p *C.clk_rule

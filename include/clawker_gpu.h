@@ -181,11 +181,19 @@ int clk_dns_gc(clk_engine *e, uint32_t now);
 /* ---- rule compiler (internal/firewall/{rules,coredns,envoy}.go) --- */
 
 /* config.EgressRule, internal/config/schema.go:131-138 (path rules are not on this path) */
-typedef struct clk_rule {
+typedef struct clk_path_rule {   /* config.PathRule schema.go:124-127 */
+    const char *path;            /* URL path prefix                                        */
+    const char *action;          /* "allow" (case-insensitive); anything else denies       */
+} clk_path_rule;
+
+typedef struct clk_rule {        /* config.EgressRule schema.go:131-138 */
     const char *dst;
     const char *proto;           /* "" / NULL = default tls (rules.go:113-125)            */
     int32_t     port;            /* 0 = default                                            */
     const char *action;          /* "" / NULL = allow                                      */
+    const char *path_default;    /* "" / NULL / "deny" = deny unmatched paths (envoy.go:594-604) */
+    const clk_path_rule *path_rules;   /* proto http: Host + path-prefix stage (F3); NULL = allow "/" */
+    uint32_t    n_path_rules;
 } clk_rule;
 
 typedef struct clk_ports {       /* firewall.EnvoyPorts envoy.go:12-16 */

@@ -76,6 +76,7 @@ class Oracle:
         L.orc_add_cidr.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.orc_add_zone.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_add_sni.argtypes = [C.c_void_p, C.c_char_p]
+        L.orc_add_http_vhost.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.orc_classify_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
                                          C.c_uint32, C.c_void_p, C.c_int]
         L.orc_classify_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
@@ -122,6 +123,8 @@ class Oracle:
             L.orc_add_zone(self.t, z.encode())
         for s in tables.get("snis", []):
             L.orc_add_sni(self.t, s.encode())
+        for domains, routes in tables.get("http", []):                 # [(domains, [(prefix, allow), ...]), ...] in config order
+            L.orc_add_http_vhost(self.t, "\n".join(domains).encode(), "\n".join(("A" if a else "D") + p for p, a in routes).encode())
         return self
 
     # ---- classification ---------------------------------------------------------------

@@ -15,11 +15,13 @@ INTERNAL_HOSTS = ["docker.internal", "otel-collector", "jaeger", "prometheus", "
 
 
 @dataclass
-class EgressRule:          # internal/config/schema.go:131-138 (path rules are off this path)
+class EgressRule:          # internal/config/schema.go:124-138
     dst: str
     proto: str = ""
     port: int = 0
     action: str = ""
+    path_rules: list = field(default_factory=list)     # [(path, action), ...]   PathRule schema.go:124-127
+    path_default: str = ""
 
 
 def domain_hash(domain: str) -> int:
@@ -144,7 +146,7 @@ def normalize_rule(r: EgressRule) -> EgressRule:
     port = r.port
     if port == 0 and proto.lower() == "tls":
         port = 443
-    return EgressRule(r.dst, proto, port, action)
+    return EgressRule(r.dst, proto, port, action, list(r.path_rules), r.path_default)
 
 
 def normalize_and_dedup(rules):
@@ -225,6 +227,34 @@ def http_domains(dst: str, exact_domains) -> list:
     return [d, d + ":*"]
 
 
+def http_rules(rules):
+    """Rule classification of GenerateEnvoyConfig, envoy.go:176-209: what lands in httpRules (port 0 -> 80)."""
+    out = []
+    for r in rules:
+        if r.action.lower() not in ("allow", "") or is_ip_or_cidr(r.dst) or r.proto.lower() != "http":
+            continue
+        out.append(EgressRule(r.dst, r.proto, r.port or 80, r.action, list(r.path_rules), r.path_default))
+    return out
+
+
+def http_routes(r: EgressRule) -> list:
+    """buildHTTPFilterChain / buildHTTPRoutes, envoy.go:403-425,566-607: [(prefix, allow)] in match order."""
+    if not r.path_rules:
+        return [("/", True)]
+    routes = [(p, a.lower() == "allow") for p, a in r.path_rules]          # strings.EqualFold(pr.Action, "allow")
+    d = r.path_default.lower()
+    routes.append(("/", not (d == "" or d == "deny")))
+    return routes
+
+
+def http_vhosts(rules) -> list:
+    """http_egress_routes virtual hosts in config order (the trailing deny_all host "*" is implicit):
+    [(domains, routes)], envoy.go:403-470 with httpExactDomains of :222-227."""
+    hs = http_rules(rules)
+    exact = {normalize_domain(r.dst) for r in hs if not is_wildcard_domain(r.dst)}
+    return [(http_domains(r.dst, exact), http_routes(r)) for r in hs]
+
+
 def tls_rules(rules):
     """Rule classification of GenerateEnvoyConfig, envoy.go:176-209: what lands in tlsRules."""
     out = []
@@ -278,6 +308,7 @@ class Compiled:
     routes: dict = field(default_factory=dict)     # (domain_hash, dst_port) -> envoy_port
     mappings: list = field(default_factory=list)
     cidrs: list = field(default_factory=list)
+    http: list = field(default_factory=list)       # [(domains, [(prefix, allow)])]
     warnings: int = 0
 
 
@@ -285,6 +316,8 @@ def compile_rules(rules, tcp_port_base: int = 10001) -> Compiled:
     """ensureConfigs + syncRoutes, internal/firewall/manager.go:753-836,1356-1377:
     normalizeAndDedup -> Corefile zones, Envoy server_names, route_map rows."""
     rules = [r if isinstance(r, EgressRule) else EgressRule(**r) for r in rules]
+    for r in rules:                                # path rules as (path, action) pairs or {"path":, "action":} dicts
+        r.path_rules = [(x["path"], x.get("action", "")) if isinstance(x, dict) else (x[0], x[1]) for x in r.path_rules]
     rs, w = normalize_and_dedup(rules)
     c = Compiled(warnings=w)
     c.zones = corefile_zones(rs)
@@ -293,4 +326,5 @@ def compile_rules(rules, tcp_port_base: int = 10001) -> Compiled:
     for dst, port, eport in c.mappings:            # later duplicates overwrite (map Update, manager.go:1367-1374)
         c.routes[(domain_hash(dst), port)] = eport
     c.cidrs = cidr_rules(rs)
+    c.http = http_vhosts(rs)
     return c

@@ -13,7 +13,7 @@ def oracle_tables(w: capture.Workload, with_cidrs: bool = True) -> dict:
     """Neutral table set for the oracle: base tables + what the (Python-restated) rule compiler derives."""
     c = rules_oracle.compile_rules(w.rules)
     t = dict(w.tables)
-    t["zones"], t["snis"], t["routes"] = c.zones, c.snis, dict(c.routes)
+    t["zones"], t["snis"], t["routes"], t["http"] = c.zones, c.snis, dict(c.routes), list(c.http)
     t["cidrs"] = list(c.cidrs) if with_cidrs else []
     return t
 
