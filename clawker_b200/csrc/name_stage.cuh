@@ -148,8 +148,16 @@ __device__ __noinline__ int dns_zone_select(const DevTables &T, const uint8_t *m
                 S1 = '.' + NAME_B1 * S1; S2 = '.' + NAME_B2 * S2;
             }
             if (!found) return 0;
+            // byte confirmation of the one hash hit: the dotted form of the suffix is the wire bytes with every
+            // length octet (known from lm) read as '.', so it is one flat loop, no label walk
             const uint8_t *str = T.names + hit.str_off;
-            if (str[0] == hit_len && dns_name_equals(m, mlen, hit_off, str + 1, hit_len)) { *zone_hash = hit.val; return 1; }
+            bool same = str[0] == hit_len;
+            for (uint32_t k = 0; same && k < hit_len; k++) {
+                const uint32_t pos = hit_off + 1 + k;
+                const uint32_t ch = ((lm >> (pos - off)) & 1ull) ? (uint32_t)'.' : lower(gb(m + pos));
+                same = str[1 + k] == ch;
+            }
+            if (same) { *zone_hash = hit.val; return 1; }
             return dns_zone_select_exact(T, m, mlen, off, after, zone_hash);
         }
     }
