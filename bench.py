@@ -328,7 +328,7 @@ def run_gpu(args) -> None:
             "metric": METRIC, "value": round(value, 1), "unit": "Mpackets/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": spec["desc"], "packets_per_gpu_per_step": n, "rules": len(w.rules), "layout": "varlen (16 B aligned frames + u32 offsets)" if varlen else "64 B slots",
+            "config": {"workload": spec["desc"], "packets_per_gpu_per_step": n, "egress_rules": len(w.rules), "table_rows": {"dns_cache": e.map_count(2), "route_map": e.map_count(3), "cidr": e.map_count(7), "containers": e.map_count(0)}, "layout": "varlen (16 B aligned frames + u32 offsets)" if varlen else "64 B slots",
                        "l2_policy": f"inputs_larger_than_l2 ({n * bytes_per_packet / 1e6:.0f} MB per step vs 126 MB L2)",
                        "parallelism": (f"packet shards x{world}, tables replicated, no data-path collective; per step 1 NCCL all-gather of per-container totals "
                                        f"({trow * 32} B per GPU, side stream, {reserved} SMs reserved); per-key metrics_map merge on read, outside the timed region "
