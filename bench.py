@@ -41,6 +41,9 @@ WORKLOADS = {
                  desc="10M-packet synthetic pcap (64 B slots) incl. 2 % IPv6 + 0.5 % non-IP, 1k IP/CIDR rules, 8 containers"),
     "c3": dict(n=100_000_000, gen=1_000_000, layout="varlen", cfg="c3",
                desc="100M packets incl. DNS + TLS-SNI (70/10/5/15 % header-only/DNS query/DNS answer/ClientHello), 10k-domain allowlist, name stage on"),
+    # c3 plus the plaintext-HTTP Host / path-prefix stage: every 8th domain also has an http rule
+    "c3h": dict(n=100_000_000, gen=1_000_000, layout="varlen", cfg="c3h", mix5=(0.64, 0.10, 0.05, 0.13, 0.08),
+                desc="100M packets incl. DNS + TLS-SNI + plaintext HTTP (64/10/5/13/8 % header-only/DNS query/DNS answer/ClientHello/HTTP request), 10k-domain allowlist, name stage on"),
     "c5": dict(n=100_000_000, gen=2_000_000, layout="slots", cfg="c5:1000", desc="64 B min-size packet flood, 100M packets/GPU"),
 }
 # Algorithmic bytes per packet: captured bytes + 4 B verdict (+ 4 B offset in varlen mode).
@@ -93,7 +96,7 @@ def make_batch(workload: str, rank: int):
     w = capture.make_workload(spec["cfg"])
     if spec["layout"] == "slots":
         return w, (capture.gen_slots(w, spec["gen"], seed=2 + 1000 * rank, **spec.get("mix", {})), None), spec
-    blob, offs, _ = capture.gen_varlen(w, spec["gen"], seed=3 + 1000 * rank, pool=8192)
+    blob, offs, _ = capture.gen_varlen(w, spec["gen"], seed=3 + 1000 * rank, pool=8192, **({"mix": spec["mix5"]} if "mix5" in spec else {}))
     return w, (blob, offs), spec
 
 

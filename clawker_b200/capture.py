@@ -131,6 +131,9 @@ def make_workload(config: str, seed: int | None = None, n_rules: int | None = No
     800 dns_cache IPs incl. 200 route rows + 200 CIDRs, 8 containers), 'c3' (10k-domain allowlist, 20 %
     wildcard), 'c4' (100k rules), 'c5:<entries>' (rule-table sweep)."""
     name = config.split(":")[0]
+    with_http = name == "c3h"                           # c3 + plaintext-HTTP rules for every 8th domain (SURVEY 8(f) F3)
+    if with_http:
+        name = "c3"
     seed = {"c1": 1, "c2": 2, "c3": 3, "c4": 4, "c5": 5}[name] if seed is None else seed
     rng = np.random.Generator(np.random.PCG64(seed))
     if name == "c1":
@@ -176,6 +179,12 @@ def make_workload(config: str, seed: int | None = None, n_rules: int | None = No
             port = 20000 + i
         seen_r.add((d, port))
         rules.append({"dst": d, "proto": proto, "port": port, "action": "allow"})
+    if with_http:
+        for i, d in enumerate(domains[::8]):
+            r = {"dst": ("." + d) if wildcard[i * 8] else d, "proto": "http", "port": 80, "action": "allow"}
+            if i % 3 == 0:
+                r.update(path_rules=[("/api/", "allow"), ("/admin", "deny")], path_default="deny" if i % 2 else "allow")
+            rules.append(r)
     # a few deny rules and duplicates that the compiler must ignore
     rules.append({"dst": "blocked.example.org", "proto": "tls", "port": 443, "action": "deny"})
     if domains:
@@ -476,7 +485,7 @@ def frame(src: int, dst: int, proto: int, sport: int, dport: int, payload: bytes
 def gen_varlen(w: Workload, n: int, seed: int = 0, pool: int = 4096,
                mix=(0.70, 0.10, 0.05, 0.15)) -> tuple[np.ndarray, np.ndarray, dict]:
     """Config-3 style capture: `mix` = fractions of (64 B TCP/UDP/other headers, DNS queries, DNS answers
-    arriving at CoreDNS, TLS ClientHellos).  Payloads come from seeded pools of `pool` distinct messages;
+    arriving at CoreDNS, TLS ClientHellos[, plaintext HTTP requests]).  Payloads come from seeded pools of `pool` distinct messages;
     per-packet L3/L4 fields are drawn independently.  Returns (blob, offs16, info)."""
     rng = np.random.Generator(np.random.PCG64(seed * 1000003 + 29))
     domains, wildcard = w.meta["domains"], w.meta["wildcard"]
@@ -518,7 +527,21 @@ def gen_varlen(w: Workload, n: int, seed: int = 0, pool: int = 4096,
         return np.frombuffer(b"".join(p), dtype=np.uint8), st[:-1], ln
 
     pools = [pool_arrays(q_pool), pool_arrays(a_pool), pool_arrays(t_pool)]
-    cls = rng.choice(4, size=n, p=list(mix)).astype(np.int8)
+    if len(mix) == 5:                                   # after the other pools: a 4-class mix draws exactly what it always drew
+        h_pool = []
+        paths = ["/", "/api/v1/items", "/api/", "/admin/login", "/index.html", "/static/app.js?v=3", "/healthz"]
+        for _ in range(pool):
+            host = pick_name(0.45, 0.2, 0.35)
+            if rng.random() < 0.15:
+                host += ":%d" % int(rng.choice([80, 8080, 3000]))
+            hdrs = [b"User-Agent: curl/8.5.0", b"Accept: */*"] if rng.random() < 0.7 else [b"Accept-Encoding: gzip", b"Connection: keep-alive", b"X-Request-Id: " + bytes(rng.integers(97, 123, size=24, dtype=np.uint8))]
+            host_line = b"Host: " + _mixed_case(rng, host).encode()
+            pos = int(rng.integers(0, len(hdrs) + 1))
+            lines = hdrs[:pos] + [host_line] + hdrs[pos:]
+            h_pool.append(("%s %s HTTP/1.1\r\n" % (str(rng.choice(["GET", "GET", "POST", "HEAD"])), paths[int(rng.integers(0, len(paths)))])).encode()
+                          + b"\r\n".join(lines) + b"\r\n\r\n")
+        pools.append(pool_arrays(h_pool))
+    cls = rng.choice(len(mix), size=n, p=list(mix)).astype(np.int8)
     f = _l34_fields(w, n, rng, v6_frac=0.01, nonip_frac=0.002)
     pidx = rng.integers(0, pool, size=n)
     pay_len = np.zeros(n, dtype=np.int64)
@@ -539,7 +562,13 @@ def gen_varlen(w: Workload, n: int, seed: int = 0, pool: int = 4096,
     c3 = (cls == 3) & v4
     f["proto"] = np.where(c3, 6, f["proto"]).astype(np.uint8)
     f["dport"] = np.where(c3 & (rng.random(n) < 0.9), 443, f["dport"])
-    for k, c in enumerate((c1, c2, c3)):
+    classes = [c1, c2, c3]
+    if len(mix) == 5:                                   # class 4: plaintext HTTP request -> TCP dport 80
+        c4 = (cls == 4) & v4
+        f["proto"] = np.where(c4, 6, f["proto"]).astype(np.uint8)
+        f["dport"] = np.where(c4, 80, f["dport"])
+        classes.append(c4)
+    for k, c in enumerate(classes):
         blobk, stk, lnk = pools[k]
         pay_len = np.where(c, lnk[pidx], pay_len)
         pay_src = np.where(c, stk[pidx], pay_src)
@@ -560,7 +589,7 @@ def gen_varlen(w: Workload, n: int, seed: int = 0, pool: int = 4096,
         idx = offs[lo:hi, None] + np.arange(64)[None, :]
         blob[idx.ravel()] = hb.ravel()
         # payloads
-        for k, c in enumerate((c1, c2, c3)):
+        for k, c in enumerate(classes):
             m = np.flatnonzero(c[lo:hi]) + lo
             if m.size == 0:
                 continue
@@ -573,7 +602,7 @@ def gen_varlen(w: Workload, n: int, seed: int = 0, pool: int = 4096,
             srci = pay_src[m][rep] + within
             # payload overwrites the zero padding / tail of the 64 B header template
             blob[dsti] = blobk[srci]
-    info = {"classes": np.bincount(cls, minlength=4).tolist(), "bytes": int(offs[-1]), "pool": pool}
+    info = {"classes": np.bincount(cls, minlength=len(mix)).tolist(), "bytes": int(offs[-1]), "pool": pool}
     return blob, (offs // 16).astype(np.uint32), info
 
 

@@ -734,11 +734,11 @@ int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, u
     int rc = ensure_published(e); if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     LaunchInfo li = { 0, 0, 0 };
-    cudaEventRecord(e->ev0, st);
+    if (!stream) cudaEventRecord(e->ev0, st);                 // a caller that brings its own stream brings its own events
     CUDA_TRY(e, e->work_rare[3].ensure((n + (1u << 20)) * 4)); // per-CTA regions (packets of the CTA's tiles); grows only for larger batches
     const char *err = launch_slots(e->T, d_pkts, stride, n, flags, (uint32_t *)d_verdicts, st, e->loader, e->stages,
                                    (uint32_t *)e->work_rare[3].p + 2, (uint32_t *)e->work_rare[3].p, &li);
-    cudaEventRecord(e->ev1, st);
+    if (!stream) cudaEventRecord(e->ev1, st);
     return finish_launch(e, err, li);
 }
 
@@ -750,9 +750,9 @@ int clk_classify_varlen_dev(clk_engine *e, const void *d_pkts, const void *d_off
     int rc = ensure_published(e); if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     LaunchInfo li = { 0, 0, 0 };
-    cudaEventRecord(e->ev0, st);
+    if (!stream) cudaEventRecord(e->ev0, st);                 // a caller that brings its own stream brings its own events
     const char *err = launch_varlen(e->T, d_pkts, (const uint32_t *)d_offs16, n, flags, (uint32_t *)d_verdicts, st, &li);
-    cudaEventRecord(e->ev1, st);
+    if (!stream) cudaEventRecord(e->ev1, st);
     return finish_launch(e, err, li);
 }
 

@@ -362,7 +362,8 @@ int clk_totals_merge(clk_engine *e, const void *d_blocks, uint32_t n_blocks, clk
 /* ---- introspection for benches ------------------------------------------------ */
 typedef struct clk_stats {
     uint64_t kernel_launches;    /* classification kernels launched so far            */
-    float    last_kernel_ms;     /* CUDA-event duration of the last classify kernel   */
+    float    last_kernel_ms;     /* CUDA-event duration of the last *_dev classify kernel launched
+                                    on the engine's own stream (stream == NULL)                    */
     uint32_t sm_count;
     uint32_t last_grid;
     uint32_t last_block;

@@ -103,3 +103,18 @@ def test_gpu_matches_oracle(seed):
     e.compile_rules(HC.RULES)
     e.publish()
     assert_same_verdicts(e.classify_varlen(blob, offs, flags=abi.F_NAME_STAGE), want, f"http cases (seed {seed})")
+
+
+@pytest.mark.gpu
+def test_gpu_matches_oracle_on_the_c3h_mix():
+    """The bench workload with plaintext HTTP in the mix (bench.py --workload c3h), at a size the oracle does in seconds."""
+    from util import assert_same_metrics, assert_same_verdicts, make_engine, oracle_tables
+    w = capture.make_workload("c3h", n_rules=2000)
+    blob, offs, info = capture.gen_varlen(w, 300_000, seed=9, pool=2048, mix=(0.64, 0.10, 0.05, 0.13, 0.08))
+    assert info["classes"][4] > 20_000
+    want, wm = oracle.Oracle("port").load(oracle_tables(w)).classify(blob, offs, flags=abi.F_NAME_STAGE)
+    names = abi.verdict_fields(want)["name"]
+    assert (names == 1).sum() > 10_000 and (names == 2).sum() > 10_000
+    e = make_engine(w)
+    assert_same_verdicts(e.classify_varlen(blob, offs, flags=abi.F_NAME_STAGE), want, "c3h mix")
+    assert_same_metrics(e.counters(), wm, "c3h mix")
