@@ -295,6 +295,10 @@ def run_gpu(args) -> None:
     h_pk = engine.pinned_empty(hp.size).reshape(hp.shape)
     h_pk[...] = hp
     h_v = engine.pinned_empty(n_e2e * 4).view(np.uint32)
+    if varlen:                                                     # the offsets ride in the pinned ring with the frames
+        h_off = engine.pinned_empty(ho.size * 4).view(np.uint32)
+        h_off[...] = ho
+        ho = h_off
     h2d_bytes = int(hp.size) + (int(ho.size) * 4 if varlen else 0)
 
     def e2e_call():

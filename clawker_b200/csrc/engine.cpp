@@ -782,8 +782,9 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
             uint64_t b0 = (uint64_t)offs16[done] * 16, b1 = (uint64_t)offs16[done + cnt] * 16;
             CUDA_TRY(e, e->work_pkts[s].ensure(b1 - b0 + 16));
             CUDA_TRY(e, e->work_offs[s].ensure((cnt + 1) * 4));
-            CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+            // offsets first: if they sit in pageable memory the (blocking, staged) copy is short and does not wait behind the frames
             CUDA_TRY(e, cudaMemcpyAsync(e->work_offs[s].p, offs16 + done, (cnt + 1) * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + b0, b1 - b0, cudaMemcpyHostToDevice, st));
             // offsets stay absolute: bias the base pointer instead of rewriting them
             err = launch_varlen(e->T, (const uint8_t *)e->work_pkts[s].p - b0, (const uint32_t *)e->work_offs[s].p, cnt, flags, (uint32_t *)e->work_verd[s].p, st, &li);
         } else {
