@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
             __syncwarp();
         }
         if (do_metrics) metric_warp_emit(T, ag, hm, mk);
-        if (qn >= 32) {                                                      // hand 32 rare packets to k_slots_rare
+        if (qn >= 32) {                                                      // move 32 rare frames to this CTA's region of rare_q
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(cta_cnt, 32u);
             base = __shfl_sync(0xffffffffu, base, 0);

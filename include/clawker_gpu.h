@@ -333,7 +333,8 @@ int clk_dns_answers(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, 
  * Copies up to cap rows; *n = rows present. */
 int clk_counters_read(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n);
 int clk_counters_reset(clk_engine *e);
-/* Fixed-size device block for the one collective of the multi-GPU path: the engine's
+/* Per-key merge across GPUs (run when the merged map is read; the per-batch form is clk_totals_*
+ * below).  Fixed-size device block: the engine's
  * metric table exported compacted into `rows` x 24 B (row 0 is a header whose `count` is the number
  * of clk_metric rows that follow) in a caller-provided DEVICE buffer; after the caller's ncclAllGather,
  * clk_counters_import sums `n_blocks` gathered blocks (device pointer) into the engine's
