@@ -253,3 +253,34 @@ func (e *Engine) TotalsMerge(dBlocks unsafe.Pointer, nBlocks uint32) ([]Total, e
 	err = e.err(C.clk_totals_merge(e.h, dBlocks, C.uint32_t(nBlocks), (*C.clk_total)(unsafe.Pointer(&out[0])), C.uint32_t(len(out)), &n))
 	return out[:int(n)], err
 }
+
+// StateSave / StateLoad: the pinned state shared with the ebpf-manager verbs (the bpffs analogue).
+func (e *Engine) StateSave(path string) error {
+	p := C.CString(path)
+	defer C.free(unsafe.Pointer(p))
+	return e.err(C.clk_state_save(e.h, p))
+}
+
+func (e *Engine) StateLoad(path string) error {
+	p := C.CString(path)
+	defer C.free(unsafe.Pointer(p))
+	return e.err(C.clk_state_load(e.h, p))
+}
+
+// ClassifyPcap classifies every frame of a classic pcap file (read, packed and classified in overlapped chunks).
+func (e *Engine) ClassifyPcap(path string, flags uint32) ([]uint32, error) {
+	p := C.CString(path)
+	defer C.free(unsafe.Pointer(p))
+	var n C.uint64_t
+	if rc := C.clk_classify_pcap(e.h, p, C.uint32_t(flags), nil, 0, &n); rc != C.CLK_OK {
+		return nil, fmt.Errorf("clawker_gpu: %s (%d)", C.GoString(C.clk_pcap_last_error()), int(rc))
+	}
+	out := make([]uint32, int(n))
+	if n == 0 {
+		return out, nil
+	}
+	if rc := C.clk_classify_pcap(e.h, p, C.uint32_t(flags), (*C.uint32_t)(unsafe.Pointer(&out[0])), n, &n); rc != C.CLK_OK {
+		return nil, fmt.Errorf("clawker_gpu: %s (%d)", C.GoString(C.clk_pcap_last_error()), int(rc))
+	}
+	return out[:int(n)], nil
+}
