@@ -101,3 +101,10 @@ def test_product_never_imports_oracle():
         if p.suffix in (".py", ".cpp", ".cu", ".cuh", ".h") and p.is_file():
             txt = p.read_text()
             assert "oracle" not in txt.replace("test oracle", "").lower() or p.name == "capture.py", p
+
+
+def test_graft_entry_build_runs():
+    """The driver's "does it build" check: every extension compiles for sm_100a and every declared symbol resolves."""
+    import __graft_entry__ as g
+    g.build()
+    assert engine.LIB_PATH.exists() and engine.CLI_PATH.exists()
