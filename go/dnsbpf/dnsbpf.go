@@ -10,6 +10,7 @@ import (
 	"github.com/coredns/caddy"
 	"github.com/coredns/coredns/core/dnsserver"
 	"github.com/coredns/coredns/plugin"
+	corelog "github.com/coredns/coredns/plugin/pkg/log"
 	"github.com/coredns/coredns/plugin/pkg/nonwriter"
 	"github.com/miekg/dns"
 
@@ -17,6 +18,8 @@ import (
 )
 
 const pluginName = "dnsbpf"
+
+var warn = corelog.NewWithPlugin(pluginName).Warningf // cache-write failures are logged, never fatal to the query
 
 // MapWriter is the interface for writing dns_cache rows.
 type MapWriter interface {
@@ -28,7 +31,7 @@ type EngineMap struct{ M *clawkerebpf.Manager }
 
 func (b EngineMap) Update(ip, domainHash, ttlSeconds uint32) {
 	if err := b.M.UpdateDNSCache(ip, domainHash, ttlSeconds); err != nil {
-		log.Warningf("updating dns_cache for ip=%s hash=%d: %v", clawkerebpf.Uint32ToIP(ip), domainHash, err)
+		warn("updating dns_cache for ip=%s hash=%d: %v", clawkerebpf.Uint32ToIP(ip), domainHash, err)
 	}
 }
 
