@@ -121,3 +121,37 @@ def test_state_file_roundtrip_and_rejects_garbage(tmp_path):
         g.state_load(str(tmp_path / "missing.pin"))
     small = engine.Engine(host_only=True, max_routes=0, max_containers=0)
     small.state_load(p)                                                             # 0 = reference defaults: fits
+
+
+def test_state_loader_survives_corruption(tmp_path):
+    """Random truncations and byte flips of a valid state file: an error or a clean load, never a crash or a hang."""
+    import numpy as np
+    e = ebpf.Manager(engine.Engine(host_only=True))
+    for cg in range(1, 20):
+        e.Enable(cg, "/x", ebpf.NewContainerConfig("10.0.0.2", "10.0.0.3", "10.0.0.1", "10.0.0.0/24", "", 0, 10000))
+        e.BindEndpoint("10.0.0.%d" % (cg + 10), cg)
+    e.e.compile_rules([{"dst": "d%d.example.com" % i, "proto": ["tls", "tcp", "http"][i % 3], "port": [443, 22, 80][i % 3],
+                        "path_rules": [("/a", "allow")] if i % 3 == 2 else []} for i in range(40)] + [{"dst": "10.%d.0.0/16" % i} for i in range(10)])
+    p = str(tmp_path / "maps.pin")
+    e.e.state_save(p)
+    raw = bytearray(open(p, "rb").read())
+    rng = np.random.Generator(np.random.PCG64(5))
+    g = engine.Engine(host_only=True)
+    ok = bad = 0
+    for _ in range(300):
+        b = bytearray(raw)
+        if rng.random() < 0.5:
+            b = b[: int(rng.integers(0, len(b)))]
+        for _k in range(int(rng.integers(0, 6))):
+            if b:
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        q = str(tmp_path / "fuzz.pin")
+        open(q, "wb").write(bytes(b))
+        try:
+            g.state_load(q)
+            ok += 1
+        except engine.ClkError:
+            bad += 1
+    assert ok + bad == 300 and bad > 100
+    g.state_load(p)                                                                  # and the intact file still loads
+    assert g.map_rows(abi.MAP_CONTAINER) == e.e.map_rows(abi.MAP_CONTAINER)

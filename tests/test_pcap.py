@@ -87,3 +87,25 @@ def test_classify_pcap_equals_classify_varlen(tmp_path):
     want, _ = oracle.Oracle("port").load(oracle_tables(w)).classify(blob, offs, flags=1)
     assert_same_verdicts(e.classify_pcap(str(tmp_path / "c3.pcap"), flags=1), want, "pcap file")
     assert_same_verdicts(e.classify_varlen(blob, offs, flags=1), want, "same frames, host buffers")
+
+
+def test_pack_survives_corruption(tmp_path):
+    """Random truncations and byte flips of a valid capture: frames or an error, never a crash; offsets stay monotonic."""
+    engine.build_library()
+    fr = _frames()
+    _write(tmp_path / "ok.pcap", fr)
+    raw = open(tmp_path / "ok.pcap", "rb").read()
+    rng = np.random.Generator(np.random.PCG64(9))
+    for _ in range(200):
+        b = bytearray(raw)
+        if rng.random() < 0.5:
+            b = b[: int(rng.integers(0, len(b)))]
+        for _k in range(int(rng.integers(0, 8))):
+            if b:
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        open(tmp_path / "fz.pcap", "wb").write(bytes(b))
+        try:
+            blob, offs, _ = _all(tmp_path / "fz.pcap", cap_bytes=1 << 20, cap_frames=4096)
+        except engine.ClkError:
+            continue
+        assert np.all(np.diff(offs.astype(np.int64)) >= 4) and int(offs[-1]) * 16 == blob.size

@@ -163,3 +163,53 @@ def test_zone_to_domain():
     for z, d in V.ZONE_TO_DOMAIN:
         assert dnsbpf.zone_to_domain(z) == d
     assert dnsbpf.Handler("x.", None).Name() == "dnsbpf"
+
+
+# ---- randomized: the C++ rule compiler (product) against the Python restatement ------------------------------
+def _random_rules(rng, n):
+    labels = ["api", "www", "cdn", "a", "b-c", "x_y", "GitHub", "example", "io", "com", "org", "co.uk", "internal", "docker"]
+    protos = ["", "tls", "TLS", "tcp", "ssh", "http", "HTTP", "udp"]
+    actions = ["", "allow", "Allow", "deny", "DENY", "log"]
+    out = []
+    for _ in range(n):
+        u = rng.random()
+        if u < 0.08:
+            dst = "%d.%d.%d.%d" % tuple(rng.integers(1, 255, size=4))
+        elif u < 0.16:
+            dst = "%d.%d.%d.0/%d" % (*rng.integers(1, 255, size=3), int(rng.integers(8, 33)))
+        elif u < 0.20:
+            dst = ["", ".", "..", "*.example.com", "a b.com", "bad:port.com", "2001:db8::1", "::ffff:10.0.0.1", "10.0.0.0/33"][int(rng.integers(0, 9))]
+        else:
+            k = int(rng.integers(1, 4))
+            dst = ".".join(labels[int(i)] for i in rng.integers(0, len(labels), size=k))
+            if rng.random() < 0.25:
+                dst = "." + dst
+            if rng.random() < 0.1:
+                dst += "."
+        r = {"dst": dst, "proto": protos[int(rng.integers(0, len(protos)))], "port": int(rng.choice([0, 0, 22, 80, 443, 8080, 8443])),
+             "action": actions[int(rng.integers(0, len(actions)))]}
+        if rng.random() < 0.3:
+            r["path_rules"] = [(["/", "/api", "/api/v1", "/admin", "", "/x?y"][int(rng.integers(0, 6))], actions[int(rng.integers(0, len(actions)))])
+                               for _ in range(int(rng.integers(1, 4)))]
+            r["path_default"] = ["", "deny", "allow", "ALLOW", "other"][int(rng.integers(0, 5))]
+        out.append(r)
+    return out
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_product_equals_oracle_on_random_rule_sets(eng, seed):
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    rules = _random_rules(rng, 120)
+    rules += [dict(r) for r in rules[:10]]                                       # exact duplicates
+    for r in rules:
+        assert engine.validate_dst(r["dst"]) == ro.validate_dst(r["dst"]), r["dst"]
+    c = firewall.compile_rules(eng, rules)
+    o = ro.compile_rules(rules)
+    assert c.zones == o.zones and c.server_names == o.snis and c.tcp_mappings == o.mappings and c.warnings == o.warnings
+    got_http = []
+    for line in eng.rules_dump(3):
+        d, rt = line.split("|")
+        got_http.append((d.split(","), [(x[1:], x[0] == "A") for x in rt.split(",")]))
+    assert got_http == [(d, r) for d, r in o.http]
+    assert sorted(eng.map_rows(7)) == sorted(int(a).to_bytes(4, "little") + int(m).to_bytes(4, "little") for a, m in set(o.cidrs))
