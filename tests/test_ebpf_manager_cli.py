@@ -155,3 +155,34 @@ def test_state_loader_survives_corruption(tmp_path):
     assert ok + bad == 300 and bad > 100
     g.state_load(p)                                                                  # and the intact file still loads
     assert g.map_rows(abi.MAP_CONTAINER) == e.e.map_rows(abi.MAP_CONTAINER)
+
+
+# TestValidateCgroupPath / TestCgroupID_RejectsMaliciousPath (internal/ebpf/manager_test.go:99-189,363-420), as data.
+# (The NUL-byte case cannot travel through argv; exec refuses it before the binary runs.)
+CGROUP_PATH_VECTORS = [
+    ("/sys/fs/cgroup/system.slice/docker-abc123.scope", None, "/sys/fs/cgroup/system.slice/docker-abc123.scope"),
+    ("/sys/fs/cgroup/docker/abc123", None, "/sys/fs/cgroup/docker/abc123"),
+    ("/sys/fs/cgroup//system.slice/./docker-abc.scope", None, "/sys/fs/cgroup/system.slice/docker-abc.scope"),
+    ("", "empty", None),
+    ("/sys/fs/cgroup/../etc/passwd", "'..'", None),
+    ("/sys/fs/cgroup/../etc/shadow", "'..'", None),
+    ("../../etc/passwd", "'..'", None),
+    ("/etc/passwd", "under /sys/fs/cgroup/", None),
+    ("/proc/self/environ", "under /sys/fs/cgroup/", None),
+    ("cgroup/foo", "under /sys/fs/cgroup/", None),
+    ("/sys/fs/cgroup", "under /sys/fs/cgroup/", None),
+    ("/sys/fs/cgroup/system.slice/x\ny", "illegal characters", None),
+]
+
+
+@pytest.mark.parametrize("path,want_err,cleaned", CGROUP_PATH_VECTORS)
+def test_cgroup_path_validation_reference_vectors(tmp_path, path, want_err, cleaned):
+    engine.build_library()
+    env = {k: v for k, v in os.environ.items() if k != "CLK_CGROUP_ROOT"}
+    env["CLK_PIN_PATH"] = str(tmp_path / "maps.pin")
+    r = subprocess.run([str(engine.CLI_PATH), "disable", path], env=env, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1
+    if want_err:
+        assert want_err in r.stderr, r.stderr
+    else:                                   # passes validation; the (cleaned) path simply does not exist on this box
+        assert f"opening cgroup: open {cleaned}:" in r.stderr, r.stderr
