@@ -58,13 +58,49 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled during the timed region (B200_PROFILING.md recipe).  NVML in-process
+    when it loads (a sample every few ms, no fork — spawning nvidia-smi from a thread stalls the launching thread
+    through the GIL for the length of the fork+exec, which sat inside the timed region); the nvidia-smi query of the
+    recipe otherwise.  Rows: [sm MHz, max sm MHz, hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap]."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.rows, self._halt, self._armed, self.source, self._nvml = index, [], threading.Event(), threading.Event(), None, None
+        try:                                                   # NVML is attached here, before the timed region, not in the thread
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(index)
+            smax = int(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [getattr(N, "nvmlClocksEventReason" + n, None) or getattr(N, "nvmlClocksThrottleReason" + n)
+                    for n in ("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap")]
+            int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), int(reasons(h))          # both queries must work before we commit to NVML
+            self._nvml = (N, h, smax, reasons, bits)
+        except Exception:
+            self._nvml = None
+
+    def arm(self):
+        """Start recording (the thread is created and parked earlier, so nothing but an Event.set() sits next to t0)."""
+        self._armed.set()
 
     def run(self):
+        self._armed.wait()
+        if self._halt.is_set():
+            return
+        if self._nvml is None:
+            return self._run_smi()
+        N, h, smax, reasons, bits = self._nvml
+        self.source = "nvml"
+        while not self._halt.is_set():
+            try:
+                sm, r = int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), int(reasons(h))
+                self.rows.append([str(sm), str(smax)] + ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            self._halt.wait(0.001)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._halt.is_set():
@@ -79,6 +115,7 @@ class ClockSampler(threading.Thread):
 
     def stop(self) -> dict:
         self._halt.set()
+        self._armed.set()
         self.join(timeout=6)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
@@ -86,7 +123,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
 def make_batch(workload: str, rank: int):
@@ -249,6 +286,9 @@ def run_gpu(args) -> None:
             dist.all_gather_into_tensor(d_gather, d_block)
             e.counters_import(d_gather.data_ptr(), world, side.cuda_stream)
 
+    sampler = ClockSampler(local) if rank == 0 else None          # attached and parked before the barrier: rank 0 must not start late
+    if sampler:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
     if world > 1:
@@ -258,22 +298,23 @@ def run_gpu(args) -> None:
     if world > 1:
         dist.barrier()
     launches0 = e.stats().kernel_launches
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     kern_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if sampler:
+        sampler.arm()
     t0.record(ts)
     for k in range(args.steps):
         step(kern_events[k])
     ts.wait_stream(side)
     t1.record(ts)
     torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None                   # samples of the timed region only
     if world > 1:
         dist.barrier()
     ms_total = t0.elapsed_time(t1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_events]))
+    launches = e.stats().kernel_launches - launches0               # our kernels inside the timed region (classify [+ totals])
     merge_ms = None
     if world > 1:                                                  # what one reader of the merged metrics_map costs (not a per-batch step)
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -286,7 +327,6 @@ def run_gpu(args) -> None:
         mg = e.counters(merged=True)
         for a in range(3):                                         # the two forms of the sum must agree
             assert int(tot["count"][:, a].sum()) == int(mg["count"][mg["action"] == a].sum()), "per-container totals != merged metrics_map"
-    launches = e.stats().kernel_launches - launches0
 
     # ---- end to end: host buffers through the C-ABI (H2D + kernel + D2H inside the timed region) ----
     e2e_reps = max(1, min(n, 10_000_000) // gen)
@@ -315,7 +355,6 @@ def run_gpu(args) -> None:
     for _ in range(e2e_steps):
         e2e_call()
     e2e_ms = (time.perf_counter() - tw0) * 1e3 / e2e_steps
-    clocks = sampler.stop() if sampler else None
 
     # ---- max over ranks ------------------------------------------------------------------------------
     if world > 1:
