@@ -91,6 +91,7 @@ class ClockSampler(threading.Thread):
             return self._run_smi()
         N, h, smax, reasons, bits = self._nvml
         self.source = "nvml"
+        self._halt.wait(0.0005)                                # first sample half a millisecond into the region: under load
         while not self._halt.is_set():
             try:
                 sm, r = int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), int(reasons(h))
