@@ -99,6 +99,12 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             self._halt.wait(0.001)
+        if not self.rows:                                      # a region shorter than the first wait: one sample right after it
+            try:
+                sm, r = int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), int(reasons(h))
+                self.rows.append([str(sm), str(smax)] + ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
 
     def _run_smi(self):
         self.source = "nvidia-smi"
