@@ -81,11 +81,14 @@ class ClockSampler(threading.Thread):
 
     def arm(self):
         """Start recording (the thread is created and parked earlier, so nothing but an Event.set() sits next to t0)."""
+        self._was_armed = True
         self._armed.set()
+
+    _was_armed = False
 
     def run(self):
         self._armed.wait()
-        if self._halt.is_set():
+        if not self._was_armed:                                # stopped without ever being armed
             return
         if self._nvml is None:
             return self._run_smi()
