@@ -81,3 +81,115 @@ def test_clock_sampler_never_armed_stops_cleanly():
     s = bench.ClockSampler(0)
     s.start()
     assert s.stop()["reasons"] == ["unavailable"] and not s.is_alive()
+
+
+# ---- dry run of bench.run_gpu on CPU: CUDA, NCCL and the engine replaced by fakes, to catch host-side slips -----------
+class _FakeStream:
+    cuda_stream = 1
+
+    def __init__(self, device=None):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+
+class _FakeEvent:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def elapsed_time(self, other):
+        return 0.25
+
+
+class _FakeStats:
+    kernel_launches = 0
+    metrics_dropped = 0
+
+
+class _FakeEngine:
+    def __init__(self, **kw):
+        self.kw, self.st = kw, _FakeStats()
+
+    def load_tables(self, t): pass
+    def compile_rules(self, r): pass
+    def publish(self): pass
+    def counters_block_rows(self): return 8
+    def totals_rows(self): return 4
+    def map_count(self, i): return 1
+
+    def stats(self):
+        return self.st
+
+    def _launch(self, *a):
+        self.st.kernel_launches += 1
+    classify_slots_dev = classify_varlen_dev = totals_export = counters_export = _launch
+
+    def counters_import(self, *a): pass
+
+    def classify_slots(self, pk, stride, flags, out=None): pass
+    def classify_varlen(self, pk, offs, flags, out=None): pass
+
+    def totals_merge(self, ptr, world):
+        import numpy as np
+        from clawker_b200.abi import TOTAL_DTYPE
+        t = np.zeros(1, dtype=TOTAL_DTYPE)
+        t[0] = (7, (5, 3, 0))
+        return t
+
+    def counters(self, merged=False):
+        import numpy as np
+        from clawker_b200.abi import METRIC_DTYPE
+        m = np.zeros(2, dtype=METRIC_DTYPE)
+        m[0] = (7, 1, 443, 0, 0, 5)
+        m[1] = (7, 2, 80, 1, 0, 3)
+        return m
+
+
+def _dry_run(monkeypatch, capsys, world, workload):
+    import contextlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from clawker_b200 import engine
+    cpu = torch.device("cpu")
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda i: None)
+    monkeypatch.setattr(torch.cuda, "set_stream", lambda s: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "Stream", _FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch, "device", lambda *a, **k: cpu)
+    for name in ("init_process_group", "barrier", "destroy_process_group", "all_gather_into_tensor", "all_reduce"):
+        monkeypatch.setattr(dist, name, lambda *a, **k: None)
+    monkeypatch.setattr(engine, "Engine", _FakeEngine)
+    monkeypatch.setattr(engine, "pinned_empty", lambda n: np.empty(n, dtype=np.uint8))
+    monkeypatch.setitem(bench.WORKLOADS[workload], "gen", 4096)
+    monkeypatch.setenv("WORLD_SIZE", str(world))
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", str(world), "--steps", "4", "--warmup", "3", "--workload", workload,
+                                      "--packets", "8192", "--no-cpu-baseline"])
+    bench.main()
+    return json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+
+
+def test_run_gpu_flow_single(monkeypatch, capsys):
+    d = _dry_run(monkeypatch, capsys, 1, "c2")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["gpu_launches"] == 4 and d["config"]["parallelism"] == "single GPU"
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["clocks"]["reasons"] == ["unavailable"]
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] == 8192 * 64
+
+
+def test_run_gpu_flow_multi_and_varlen(monkeypatch, capsys):
+    d = _dry_run(monkeypatch, capsys, 2, "c2")
+    assert d["n_gpus"] == 2 and d["gpu_launches"] == 8 and "4 SMs reserved" in d["config"]["parallelism"]     # classify + totals per step
+    d = _dry_run(monkeypatch, capsys, 1, "c3h")
+    assert d["roofline"]["kernel"] == "clk::k_varlen_fast" and d["config"]["layout"].startswith("varlen")
