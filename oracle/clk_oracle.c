@@ -27,6 +27,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <stdio.h>
 #include <pthread.h>
 
@@ -841,6 +842,34 @@ void orc_classify_batch(const orc_tables *t, orc_metrics *metrics, const uint8_t
         if (metrics) { orc_metrics_merge(metrics, js[k].mx); orc_metrics_free(js[k].mx); }
     }
     free(th); free(js);
+}
+
+/* The CPU-baseline form: the same sharding, but only the parallel section is timed — the threads (the CPUs the
+ * hooks would run on) and their private metrics maps (BPF_MAP_TYPE_PERCPU_HASH: one value per CPU, never merged on
+ * the hot path) exist before the clock starts, and the per-thread maps are discarded afterwards, not summed.
+ * Returns seconds from "all threads released" to "last thread done". */
+typedef struct tjob { job j; pthread_barrier_t *go; } tjob;
+static void *tjob_run(void *arg) { tjob *tj = (tjob *)arg; pthread_barrier_wait(tj->go); return job_run(&tj->j); }
+
+double orc_classify_batch_timed(const orc_tables *t, const uint8_t *pkts, const uint32_t *offs16, uint32_t stride, uint64_t n,
+                                uint32_t flags, uint32_t *verdicts, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    pthread_t *th = calloc(nthreads, sizeof *th); tjob *js = calloc(nthreads, sizeof *js);
+    pthread_barrier_t go; pthread_barrier_init(&go, NULL, (unsigned)nthreads + 1);
+    for (int k = 0; k < nthreads; k++) {
+        js[k].j = (job){ t, (flags & CLK_F_NO_METRICS) ? NULL : orc_metrics_new(), pkts, offs16, stride, n * k / nthreads, n * (k + 1) / nthreads, flags, verdicts };
+        js[k].go = &go;
+        pthread_create(&th[k], NULL, tjob_run, &js[k]);
+    }
+    struct timespec a, b;
+    pthread_barrier_wait(&go);
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    for (int k = 0; k < nthreads; k++) pthread_join(th[k], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    for (int k = 0; k < nthreads; k++) if (js[k].j.mx) orc_metrics_free(js[k].j.mx);
+    pthread_barrier_destroy(&go); free(th); free(js);
+    return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
 }
 
 void orc_classify_events(const orc_tables *t, orc_metrics *metrics, const clk_event *ev, uint64_t n, uint32_t flags, uint32_t *verdicts)

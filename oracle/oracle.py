@@ -80,6 +80,8 @@ class Oracle:
         L.orc_classify_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
                                          C.c_uint32, C.c_void_p, C.c_int]
         L.orc_classify_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.orc_classify_batch_timed.restype = C.c_double
+        L.orc_classify_batch_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int]
         L.orc_metrics_count.restype = C.c_uint32
         L.orc_metrics_count.argtypes = [C.c_void_p]
         L.orc_metrics_dump.restype = C.c_uint32
@@ -150,6 +152,21 @@ class Oracle:
         m = self.lib.orc_metrics_new() if metrics else None
         self.lib.orc_classify_batch(self.t, m, pkts.ctypes.data, op, stride, n, flags, verd.ctypes.data, nthreads)
         return verd, (self._metrics_out(m) if metrics else None)
+
+    def classify_timed(self, pkts: np.ndarray, offs16: np.ndarray | None = None, stride: int = 64, flags: int = 0,
+                       nthreads: int = 1, verd: np.ndarray | None = None) -> float:
+        """CPU-baseline form: seconds spent in the parallel section only (threads and their private PERCPU metrics
+        maps exist before the clock starts; the per-thread maps are discarded, not merged).  `verd` receives the words."""
+        pkts = np.ascontiguousarray(pkts, dtype=np.uint8)
+        if offs16 is None:
+            n, op = pkts.size // stride, None
+        else:
+            offs16 = np.ascontiguousarray(offs16, dtype=np.uint32)
+            n, op = offs16.size - 1, offs16.ctypes.data
+        if verd is None:
+            verd = np.zeros(n, dtype=np.uint32)
+        assert verd.size >= n and verd.dtype == np.uint32
+        return float(self.lib.orc_classify_batch_timed(self.t, pkts.ctypes.data, op, stride, n, flags, verd.ctypes.data, nthreads))
 
     def classify_events(self, events: np.ndarray, flags: int = 0):
         events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
