@@ -50,8 +50,9 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_shards_and_counter_allgather():
-    world, port = 2, _free_port()
+@pytest.mark.parametrize("world", [2, 4])
+def test_rank_shards_and_counter_allgather(world):
+    port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
