@@ -4,16 +4,20 @@
     python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own eBPF C on the host cores
 
-A "step" is one pass of the hot path over one batch of synthetic packets.  At N = 1 the workload is
-BASELINE.json configs[1] (10 M-packet synthetic pcap as 64-byte slots, 1k IP/CIDR rules); every rank of
-an N-GPU run classifies its own batch of the same shape (weak scaling) and the ranks' per-GPU counters
-are all-gathered once per step over NCCL.  One JSON line is printed by rank 0.
+A "step" is one pass of the hot path over one batch of synthetic packets.  The default workload is the one the
+north-star target is quoted on, BASELINE.json configs[2] ("c3": 100 M packets incl. DNS + TLS-SNI, 10k-domain
+allowlist, name stage on, variable-length frames); configs[1] ("c2": 10 M 64-byte slots, 1k IP/CIDR rules) is
+measured in the same run and reported inside the same JSON line under "also".  Every rank of an N-GPU run
+classifies its own batch of the same shape (weak scaling); the ranks' per-container counter totals are
+all-gathered once per step over NCCL.  One JSON line is printed by rank 0.
 
-Timing: CUDA events on the launch stream, W >= 3 warm-up steps, inputs (640 MB) far larger than L2, the
-max over ranks.  `value` is device-resident throughput; `e2e` is the same metric through the host-buffer
-C-ABI entry (clk_classify_slots: pinned host packets -> H2D -> kernel -> D2H verdicts inside the timed
-region).  `cpu_baseline` times the oracle (the reference's clawker.c compiled for the host when
-oracle/_ref is present) on this box's cores — the ONLY place this file touches oracle/.
+Timing: CUDA events on the launch stream, W >= 3 warm-up steps, inputs far larger than L2, the max over ranks.
+`value` is device-resident throughput of exactly K steps; `sustained` repeats the step for >= --seconds of GPU
+time; `e2e` is the same metric through the host-buffer C-ABI entry (pinned host packets -> H2D -> kernel -> D2H
+verdicts inside the timed region); `parity` compares the verdict words and the metrics_map of the benched
+batch with the CPU oracle (outside the timed region).  `cpu_baseline` / `--impl reference` time the oracle (the
+reference's clawker.c compiled for the host when oracle/_ref is present) on this box's cores — parity and those
+two legs are the ONLY places this file touches oracle/.
 """
 from __future__ import annotations
 
@@ -44,9 +48,26 @@ WORKLOADS = {
     # c3 plus the plaintext-HTTP Host / path-prefix stage: every 8th domain also has an http rule
     "c3h": dict(n=100_000_000, gen=1_000_000, layout="varlen", cfg="c3h", mix5=(0.64, 0.10, 0.05, 0.13, 0.08),
                 desc="100M packets incl. DNS + TLS-SNI + plaintext HTTP (64/10/5/13/8 % header-only/DNS query/DNS answer/ClientHello/HTTP request), 10k-domain allowlist, name stage on"),
-    "c5": dict(n=100_000_000, gen=2_000_000, layout="slots", cfg="c5:1000", desc="64 B min-size packet flood, 100M packets/GPU"),
+    # BASELINE.json configs[3]: C2 u C3 mix, 100k rules, 125 M packets per GPU (1 B over 8 GPUs)
+    "c4": dict(n=125_000_000, gen=1_000_000, layout="varlen", cfg="c4", mix=(0.85, 0.05, 0.03, 0.07),
+               desc="1B mixed TCP/UDP/DNS packets over 8 GPUs (125M per GPU; 85/5/3/7 % header-only/DNS query/DNS answer/ClientHello), 100k rules, 64 containers, name stage on"),
+    # BASELINE.json configs[4]: 64 B flood against a rule table of the given size ("c5:<entries>", --sweep runs 2^4..2^20)
+    "c5": dict(n=100_000_000, gen=2_000_000, layout="slots", cfg="c5:1024", mix=dict(v6_frac=0.0, nonip_frac=0.0),
+               desc="64 B min-size packet flood, 100M packets/GPU, rule table of 1024 entries"),
 }
+SWEEP_SIZES = [1 << k for k in range(4, 21, 2)]
 # Algorithmic bytes per packet: captured bytes + 4 B verdict (+ 4 B offset in varlen mode).
+
+
+def workload_spec(name: str) -> dict:
+    """WORKLOADS entry; "c5:<entries>" selects the rule-table size of the flood workload."""
+    if name.startswith("c5:"):
+        k = int(name.split(":")[1])
+        s = dict(WORKLOADS["c5"])
+        s["cfg"] = f"c5:{k}"
+        s["desc"] = f"64 B min-size packet flood, 100M packets/GPU, rule table of {k} entries"
+        return s
+    return WORKLOADS[name]
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -63,9 +84,10 @@ class ClockSampler(threading.Thread):
     through the GIL for the length of the fork+exec, which sat inside the timed region); the nvidia-smi query of the
     recipe otherwise.  Rows: [sm MHz, max sm MHz, hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap]."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period: float = 0.001):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt, self._armed, self.source, self._nvml = index, [], threading.Event(), threading.Event(), None, None
+        self.period = period
         try:                                                   # NVML is attached here, before the timed region, not in the thread
             import pynvml as N
             N.nvmlInit()
@@ -101,7 +123,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([str(sm), str(smax)] + ["Active" if r & b else "Not Active" for b in bits])
             except Exception:
                 pass
-            self._halt.wait(0.001)
+            self._halt.wait(self.period)
         if not self.rows:                                      # a region shorter than the first wait: one sample right after it
             try:
                 sm, r = int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), int(reasons(h))
@@ -137,13 +159,19 @@ class ClockSampler(threading.Thread):
 
 
 def make_batch(workload: str, rank: int):
-    """Synthetic capture of the named shape; `gen` unique packets tiled to n (HBM does not care)."""
+    """Synthetic capture of the named shape: `gen` unique packets (tiled to n on the device; HBM does not care —
+    the tiling is stated in config.synthetic and --untiled generates every packet)."""
     from clawker_b200 import capture
-    spec = WORKLOADS[workload]
+    spec = workload_spec(workload)
     w = capture.make_workload(spec["cfg"])
     if spec["layout"] == "slots":
         return w, (capture.gen_slots(w, spec["gen"], seed=2 + 1000 * rank, **spec.get("mix", {})), None), spec
-    blob, offs, _ = capture.gen_varlen(w, spec["gen"], seed=3 + 1000 * rank, pool=8192, **({"mix": spec["mix5"]} if "mix5" in spec else {}))
+    kw = {}
+    if "mix5" in spec:
+        kw["mix"] = spec["mix5"]
+    elif "mix" in spec:
+        kw["mix"] = spec["mix"]
+    blob, offs, _ = capture.gen_varlen(w, spec["gen"], seed=3 + 1000 * rank, pool=8192, **kw)
     return w, (blob, offs), spec
 
 
@@ -161,53 +189,96 @@ def batch_packets(batch) -> int:
     return batch[0].shape[0] if batch[1] is None else batch[1].size - 1
 
 
+def table_rows(w) -> dict:
+    """Rows behind the rule count, from the workload definition alone (so both arms print the same numbers)."""
+    return {"dns_cache": len(w.tables["dns_cache"]), "route_map": int(w.meta["n_routes"]), "cidr": int(w.meta["n_cidr"]),
+            "containers": len(w.tables["containers"]), "domains": int(w.meta["n_domains"])}
+
+
+def config_of(spec: dict, w, n: int, gen: int, world: int) -> dict:
+    """The `config` object — identical for the CUDA arm and the reference arm of the same command line."""
+    varlen = spec["layout"] == "varlen"
+    return {"workload": spec["desc"], "packets_per_gpu_per_step": n, "egress_rules": len(w.rules), "table_rows": table_rows(w),
+            "layout": "varlen (16 B aligned frames + u32 offsets)" if varlen else "64 B slots",
+            "synthetic": f"{gen} unique seeded packets per GPU tiled x{max(1, n // gen)} to the batch size",
+            "l2_policy": "inputs_larger_than_l2 (>= 640 MB per step vs 126 MB L2)",
+            "parallelism": f"packet shards x{world} (weak), tables replicated, no data-path collective; per step 1 all-gather of per-container counter totals" if world > 1 else "single GPU"}
+
+
 # ---------------------------------------------------------------------------------------------------
-def cpu_baseline(w, batch, steps: int = 1, warmup: int = 1, name_stage: bool = False) -> dict:
-    """The reference's own decision code on this box's host cores (kind "reference" = /root/reference's
-    clawker.c compiled for the host in oracle/_ref; "port" = the C restatement).  Bounded sample.  With the
-    name stage on, the CoreDNS / Envoy / dnsbpf stages around it are the oracle's restatement in both kinds
-    (third-party code, not in the reference tree)."""
+# CPU side: the oracle as checker (parity) and as baseline (cpu_baseline / --impl reference)
+# ---------------------------------------------------------------------------------------------------
+def _oracle_for(w, name_stage: bool, want_cidr: bool):
+    """Loaded oracle + its kind.  The reference object ignores IP/CIDR rules, so a workload with CIDR
+    rules is CHECKED against the port (which evaluates them, A12) and TIMED on the reference object."""
     from oracle import oracle, rules_oracle
-    kind = "reference" if oracle.have_ref() else "port"
-    o = oracle.Oracle("ref" if kind == "reference" else "port")
     c = rules_oracle.compile_rules(w.rules)
+    use_ref = oracle.have_ref() and not (want_cidr and c.cidrs)
+    o = oracle.Oracle("ref" if use_ref else "port")
     t = dict(w.tables)
-    t.update(zones=c.zones, snis=c.snis, routes=dict(c.routes), cidrs=[] if kind == "reference" else list(c.cidrs))
+    t.update(zones=c.zones, snis=c.snis, routes=dict(c.routes), cidrs=[] if use_ref else list(c.cidrs), http=list(getattr(c, "http", []) or []))
     o.load(t)
-    cores = os.cpu_count() or 1
+    return o, ("reference" if use_ref else "port")
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(w, batch, samples: int = 5, warmup: int = 1, name_stage: bool = False, target_s: float = 2.0) -> dict:
+    """The reference's own decision code on this box's host cores (kind "reference" = /root/reference's clawker.c
+    compiled for the host in oracle/_ref; "port" = the C restatement).  With the name stage on, the CoreDNS / Envoy /
+    dnsbpf stages around it are the oracle's restatement in both kinds (third-party code, not in the reference tree).
+
+    One sample = every thread (pinned, one per allowed CPU) classifies its private copy of ~0.25 M packets of the same
+    capture `repeat` times, `repeat` calibrated so a sample lasts about `target_s` seconds; the value is the MEDIAN of
+    `samples` samples (min and max reported)."""
+    o, kind = _oracle_for(w, name_stage, want_cidr=False)
+    cores = host_threads()
     npk = batch_packets(batch)
-    reps = max(1, (250_000 * cores) // npk)                         # ~0.25 M packets per thread: 10-30 CPU-seconds per step
+    reps = max(1, (250_000 * cores) // npk)
     pk, offs = tile_host(batch, reps) if reps > 1 else batch
     flags = 1 if name_stage else 0
     n_s = batch_packets((pk, offs))
     verd = np.zeros(n_s, dtype=np.uint32)
-    for _ in range(max(1, warmup)):                                 # untimed: warms the tables and the page cache
-        o.classify_timed(pk, offs, flags=flags, nthreads=cores, verd=verd)
-    # only the parallel section is timed: the threads stand for the CPUs the hooks run on and already exist, each has
-    # its own metrics map (BPF_MAP_TYPE_PERCPU_HASH) that nothing merges on the hot path
-    dt = sum(o.classify_timed(pk, offs, flags=flags, nthreads=cores, verd=verd) for _ in range(max(1, steps))) / max(1, steps)
-    sample = (f"{n_s} packets of the same capture per step, {cores} threads, per-thread metrics maps (PERCPU, not merged), "
-              "thread start-up excluded"
+    o.classify_timed2(pk, offs, flags=flags, nthreads=cores, repeat=1, verd=verd)                # cold pass: page-in, tables
+    dt1 = o.classify_timed2(pk, offs, flags=flags, nthreads=cores, repeat=1, verd=verd)          # calibration pass
+    repeat = max(1, int(round(target_s / max(dt1, 1e-4))))
+    for _ in range(max(0, warmup)):
+        o.classify_timed2(pk, offs, flags=flags, nthreads=cores, repeat=repeat, verd=verd)
+    dts = sorted(o.classify_timed2(pk, offs, flags=flags, nthreads=cores, repeat=repeat, verd=verd) for _ in range(max(1, samples)))
+    med = dts[len(dts) // 2]
+    per = n_s * repeat
+    sample = (f"{n_s} packets of the same capture x{repeat} passes per sample ({per} verdicts, ~{med:.2f} s), {cores} threads pinned one per CPU, "
+              f"thread-private copies of the input, per-thread metrics maps (PERCPU, not merged), thread start-up excluded; median of {len(dts)} samples"
               + ("; IP/CIDR extension rules are not evaluated by the reference (SURVEY R4)" if kind == "reference" else ""))
-    return {"value": round(n_s / dt / 1e6, 2), "unit": "Mpackets/s", "cores": cores, "kind": kind, "sample": sample,
-            "ms_per_step": round(dt * 1e3, 3), "packets_per_step": n_s}
+    return {"value": round(per / med / 1e6, 2), "unit": "Mpackets/s", "cores": cores, "kind": kind, "sample": sample,
+            "min": round(per / dts[-1] / 1e6, 2), "max": round(per / dts[0] / 1e6, 2), "samples": len(dts),
+            "ms_per_step": round(med * 1e3, 3), "packets_per_step": per}
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     w, batch, spec = make_batch(args.workload, 0)
     t0 = time.perf_counter()
-    base = cpu_baseline(w, batch, steps=max(1, args.steps), warmup=max(1, args.warmup), name_stage=spec["layout"] == "varlen")
-    ms, pps = base.pop("ms_per_step"), base.pop("packets_per_step")
+    base = cpu_baseline(w, batch, samples=max(1, args.steps), warmup=max(0, args.warmup), name_stage=spec["layout"] == "varlen",
+                        target_s=args.ref_sample_seconds)
+    ms = base.pop("ms_per_step")
+    base.pop("packets_per_step")
+    gen = batch_packets(batch)
+    n = spec["n"] if args.packets <= 0 else args.packets
+    n = ((n + gen - 1) // gen) * gen if spec["layout"] == "varlen" else n
     line = {
         "metric": METRIC, "impl": "reference", "value": base["value"], "unit": "Mpackets/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": spec["desc"], "packets_per_step": pps, "egress_rules": len(w.rules),
-                   "layout": "varlen (16 B aligned frames + u32 offsets)" if spec["layout"] == "varlen" else "64 B slots",
-                   "parallelism": f"host threads x{base['cores']} (the reference's CPU path; rank 0 only)"},
+        "config": config_of(spec, w, n, gen, max(world, args.gpus)),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "Mpackets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": round(time.perf_counter() - t0, 2),
@@ -215,8 +286,44 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def check_parity(e, w, batch, d_v, n: int, gen: int, varlen: bool, flags: int, run_step, threads: int) -> dict:
+    """Bit-exact check of the BENCHED batch (outside the timed region): the verdict words of the first and the last
+    whole copy of the unique packets, and — after a counters reset and one more pass — this GPU's metrics_map against
+    the oracle's (counts x the tiling factor)."""
+    import torch
+    from oracle import oracle
+    o, kind = _oracle_for(w, varlen, want_cidr=True)
+    pk, offs = batch
+    want, wm = o.classify(pk, offs, flags=flags, nthreads=threads)
+    reps = n // gen
+    blocks = sorted({0, max(0, reps - 1)})
+    checked = mism = 0
+    for b in blocks:
+        got = d_v[b * gen:(b + 1) * gen].cpu().numpy().view(np.uint32)
+        k = min(got.size, want.size)
+        mism += int((got[:k] != want[:k]).sum())
+        checked += k
+    out = {"checked": checked, "mismatches": mism, "rate": round(1.0 - mism / max(1, checked), 9), "oracle": "ref" if kind == "reference" else "port"}
+    if n == reps * gen:
+        e.counters_reset()
+        run_step()
+        torch.cuda.synchronize()
+        gm, dropped = e.counters(), int(e.stats().metrics_dropped)
+        if dropped == 0:
+            a, b = oracle.sort_metrics(gm), oracle.sort_metrics(wm)
+            same_keys = a.size == b.size and all(np.array_equal(a[f], b[f]) for f in ("cgroup_id", "domain_hash", "dst_port", "action"))
+            bad = int((a["count"] != b["count"] * reps).sum()) if same_keys else max(a.size, b.size)
+            out["counters"] = {"rows": int(a.size), "oracle_rows": int(b.size), "mismatches": bad}
+        else:
+            out["counters"] = {"rows": int(gm.size), "skipped": f"metrics_map reached max_entries ({dropped} increments dropped, as BPF_NOEXIST into a full map)"}
+        out["totals_oracle"] = [int(wm["count"][wm["action"] == a].sum()) * reps for a in range(3)]
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
-def run_gpu(args) -> None:
+def measure(args, workload: str, full: bool) -> dict:
+    """One workload on this rank's GPU: device-resident K steps (+ sustained), parity, e2e.  Returns the pieces of the
+    JSON line (rank 0) — `full` adds the sustained leg and the CPU baseline."""
     import torch
     import torch.distributed as dist
     from clawker_b200 import abi, engine
@@ -224,13 +331,7 @@ def run_gpu(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the CUDA library is the product, there is no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    w, batch, spec = make_batch(args.workload, rank)
+    w, batch, spec = make_batch(workload, rank)
     pk, offs = batch
     varlen = offs is not None
     gen = batch_packets(batch)
@@ -243,6 +344,7 @@ def run_gpu(args) -> None:
         per = int(offs[-1])
         o64 = torch.from_numpy(offs.astype(np.int64)).to(dev)
         d_offs = torch.cat([o64[:-1] + k * per for k in range(reps)] + [o64[-1:] + (reps - 1) * per]).to(torch.int32)
+        del o64
         total_bytes = int(d_pk.numel())
         if (total_bytes >> 4) >= (1 << 32):
             raise SystemExit("batch exceeds the 64 GiB reach of 16-byte offsets")
@@ -254,13 +356,14 @@ def run_gpu(args) -> None:
         d_offs = None
         bytes_per_packet = 68.0
     d_v = torch.empty(n, dtype=torch.int32, device=dev)
-    flags = 1 if varlen else 0                                     # CLK_F_NAME_STAGE on the varlen workload
+    flags = abi.F_NAME_STAGE if varlen else 0
 
     # metrics_map max_entries: 8x the reference default (common.h:173) so every key of the synthetic capture is counted;
     # keys beyond max_entries are dropped like the reference BPF_NOEXIST insert into a full map (--metrics-capacity)
     # multi-GPU: the classify kernels leave a few SMs to the side stream so the per-batch collective never delays them
     reserved = args.reserved_sms if args.reserved_sms >= 0 else (4 if world > 1 else 0)
-    e = engine.Engine(device=local, max_metrics=args.metrics_capacity, max_dns_cache=1 << 21, max_routes=1 << 16, reserved_sms=reserved)
+    e = engine.Engine(device=local, max_metrics=args.metrics_capacity, max_dns_cache=1 << 21, max_routes=1 << 16, max_containers=max(256, len(w.tables["containers"])),
+                      reserved_sms=reserved)
     e.load_tables(w.tables)
     e.compile_rules(w.rules)
     e.publish()
@@ -300,7 +403,8 @@ def run_gpu(args) -> None:
     sampler = ClockSampler(local) if rank == 0 else None          # attached and parked before the barrier: rank 0 must not start late
     if sampler:
         sampler.start()
-    for _ in range(max(3, args.warmup)):
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         step()
     if world > 1:
         side.wait_stream(ts)
@@ -326,7 +430,42 @@ def run_gpu(args) -> None:
     ms_total = t0.elapsed_time(t1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_events]))
     launches = e.stats().kernel_launches - launches0               # our kernels inside the timed region (classify [+ totals])
+
+    # ---- sustained: the same step back to back for >= --seconds of GPU time (clocks and power under real load) -----
+    sustained = None
+    if full and args.seconds > 0:
+        s2 = ClockSampler(local, period=0.02) if rank == 0 else None
+        if s2:
+            s2.start()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        est = max(ms_total / max(1, args.steps), 1e-3)
+        total_steps = max(args.steps, int(args.seconds * 1e3 / est) + 1)
+        if world > 1:                                              # every rank must run the same number of steps (one collective each)
+            tsn = torch.tensor([total_steps], dtype=torch.int64, device=dev)
+            dist.all_reduce(tsn, op=dist.ReduceOp.MAX)
+            total_steps = int(tsn.item())
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if s2:
+            s2.arm()
+        u0.record(ts)
+        for _ in range(total_steps):
+            step()
+        ts.wait_stream(side)
+        u1.record(ts)
+        torch.cuda.synchronize()
+        c2 = s2.stop() if s2 else None
+        sus_ms = u0.elapsed_time(u1)
+        if world > 1:
+            tt = torch.tensor([sus_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sus_ms = float(tt.item())
+        sustained = {"seconds": round(sus_ms / 1e3, 3), "steps": total_steps, "ms_per_step": round(sus_ms / total_steps, 4),
+                     "value": round(world * n * total_steps / sus_ms / 1e3, 1), "unit": "Mpackets/s", "clocks": c2}
+
     merge_ms = None
+    tot = None
     if world > 1:                                                  # what one reader of the merged metrics_map costs (not a per-batch step)
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         m0.record(side)
@@ -338,6 +477,25 @@ def run_gpu(args) -> None:
         mg = e.counters(merged=True)
         for a in range(3):                                         # the two forms of the sum must agree
             assert int(tot["count"][:, a].sum()) == int(mg["count"][mg["action"] == a].sum()), "per-container totals != merged metrics_map"
+
+    # ---- parity of the benched batch (outside the timed region) -------------------------------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = check_parity(e, w, batch, d_v, n, gen, varlen, flags, step, max(1, host_threads() // max(1, world)))
+        if world > 1:
+            side.wait_stream(ts)
+            torch.cuda.synchronize()
+            tot1 = e.totals_merge(d_tot_all.data_ptr(), world)     # totals gathered by the parity pass: one batch per rank since the reset
+            mine = torch.tensor([parity["checked"], parity["mismatches"], parity.get("counters", {}).get("mismatches", 0) or 0]
+                                + parity.get("totals_oracle", [0, 0, 0]), dtype=torch.int64, device=dev)
+            dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+            v = [int(x) for x in mine.tolist()]
+            parity.update(checked=v[0], mismatches=v[1], rate=round(1.0 - v[1] / max(1, v[0]), 9))
+            if "counters" in parity and "mismatches" in parity["counters"]:
+                parity["counters"]["mismatches"] = v[2]
+            got_tot = [int(tot1["count"][:, a].sum()) for a in range(3)]
+            parity["merged_totals"] = {"gathered": got_tot, "oracle_sum_over_ranks": v[3:6], "equal": got_tot == v[3:6]}
+        parity.pop("totals_oracle", None)
 
     # ---- end to end: host buffers through the C-ABI (H2D + kernel + D2H inside the timed region) ----
     e2e_reps = max(1, min(n, 10_000_000) // gen)
@@ -366,46 +524,105 @@ def run_gpu(args) -> None:
     for _ in range(e2e_steps):
         e2e_call()
     e2e_ms = (time.perf_counter() - tw0) * 1e3 / e2e_steps
+    e2e_parity = None
+    if parity is not None:                                         # the host-buffer path writes the same words
+        from oracle import oracle as _o                            # noqa: F401  (checker only)
+        o, _k = _oracle_for(w, varlen, want_cidr=True)
+        want, _ = o.classify(pk, offs, flags=flags, nthreads=max(1, host_threads() // max(1, world)), metrics=False)
+        e2e_parity = int((np.asarray(h_v[:gen]) != want[:gen]).sum()) + int((np.asarray(h_v[n_e2e - gen:]) != want[:gen]).sum())
 
     # ---- max over ranks ------------------------------------------------------------------------------
     if world > 1:
         tt = torch.tensor([ms_total, kern_ms, e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total, kern_ms, e2e_ms = (float(x) for x in tt.tolist())
+        if e2e_parity is not None:
+            ep = torch.tensor([e2e_parity], dtype=torch.int64, device=dev)
+            dist.all_reduce(ep, op=dist.ReduceOp.SUM)
+            e2e_parity = int(ep.item())
+    out = None
     if rank == 0:
         peak, how = peaks()
         ms_per_step = ms_total / args.steps
         value = world * n / ms_per_step / 1e3                     # Mpackets/s, whole job
         achieved = n * bytes_per_packet / (kern_ms * 1e-3) / 1e9
-        prof = ROOT / "profiles" / ("r01_traffic.json" if not varlen else "r01_varlen_traffic.json")
         traffic = None
-        if prof.exists():                                          # ncu dram__bytes_{read,write}.sum of one launch, scaled to this launch's packets
-            pj = json.loads(prof.read_text())
-            traffic = round(pj["dram_bytes_per_launch"] * n / pj["packets_per_launch"])
-        base = None
-        if world == 1 and not args.no_cpu_baseline:
-            base = cpu_baseline(w, batch, steps=2, warmup=1, name_stage=varlen)
-            base.pop("ms_per_step"), base.pop("packets_per_step")
-        line = {
-            "metric": METRIC, "value": round(value, 1), "unit": "Mpackets/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": spec["desc"], "packets_per_gpu_per_step": n, "egress_rules": len(w.rules), "table_rows": {"dns_cache": e.map_count(2), "route_map": e.map_count(3), "cidr": e.map_count(7), "containers": e.map_count(0)}, "layout": "varlen (16 B aligned frames + u32 offsets)" if varlen else "64 B slots",
-                       "l2_policy": f"inputs_larger_than_l2 ({n * bytes_per_packet / 1e6:.0f} MB per step vs 126 MB L2)",
-                       "parallelism": (f"packet shards x{world}, tables replicated, no data-path collective; per step 1 NCCL all-gather of per-container totals "
-                                       f"({trow * 32} B per GPU, side stream, {reserved} SMs reserved); per-key metrics_map merge on read, outside the timed region "
-                                       f"({merge_ms:.3f} ms per read)") if world > 1 else "single GPU"},
+        for cand in (("r02_varlen_traffic.json", "r01_varlen_traffic.json") if varlen else ("r02_traffic.json", "r01_traffic.json")):
+            prof = ROOT / "profiles" / cand
+            if prof.exists():                                      # ncu dram__bytes_{read,write}.sum of one launch, scaled to this launch's packets
+                pj = json.loads(prof.read_text())
+                traffic = round(pj["dram_bytes_per_launch"] * n / pj["packets_per_launch"])
+                break
+        cfg = config_of(spec, w, n, gen, world)
+        if world > 1:
+            cfg["collective"] = (f"{trow * 32} B per GPU per step on a side stream, {reserved} SMs reserved; per-key metrics_map merge on read, "
+                                 f"outside the timed region ({merge_ms:.3f} ms per read)")
+        out = {
+            "value": round(value, 1), "unit": "Mpackets/s", "ms_per_step": round(ms_per_step, 4), "config": cfg,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "peak_source": how, "kernel": "clk::k_varlen_fast" if varlen else "clk::k_slots_fast", "kernel_ms": round(kern_ms, 4),
+                         "traffic": traffic, "peak_source": how, "kernel": "clk::k_varlen_chunk" if varlen else "clk::k_slots_fast", "kernel_ms": round(kern_ms, 4),
                          "algorithmic_bytes_per_packet": round(bytes_per_packet, 2)},
             "e2e": {"value": round(world * n_e2e / e2e_ms / 1e3, 1), "unit": "Mpackets/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": n_e2e * 4, "packets_per_step": n_e2e, "ms_per_step": round(e2e_ms, 3),
+                    "bytes_per_packet_over_pcie": round((h2d_bytes + n_e2e * 4) / n_e2e, 1), "verdict_mismatches": e2e_parity,
                     "path": ("clk_classify_varlen" if varlen else "clk_classify_slots") + " (pinned host buffers, 3-stream chunked H2D/kernel/D2H)"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
             "metrics": {"max_entries": args.metrics_capacity, "rows": int(e.counters().size), "dropped_increments": int(e.stats().metrics_dropped)},
         }
-        if base:
-            line["cpu_baseline"] = base
+        if sustained:
+            out["sustained"] = sustained
+        if full and world == 1 and not args.no_cpu_baseline:
+            base = cpu_baseline(w, batch, samples=3, warmup=0, name_stage=varlen, target_s=1.0)
+            base.pop("ms_per_step"), base.pop("packets_per_step")
+            out["cpu_baseline"] = base
+    del d_pk, d_v, d_offs, d_block, d_gather, d_tot, d_tot_all, h_pk, h_v
+    e.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_gpu(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the CUDA library is the product, there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    if args.sweep:                                                 # BASELINE.json configs[4]: rule-table sweep 2^4..2^20, frac per size
+        rows = []
+        for k in SWEEP_SIZES:
+            m = measure(args, f"c5:{k}", full=False)
+            if rank == 0:
+                rows.append({"entries": k, "value": m["value"], "frac": m["roofline"]["frac"], "kernel_ms": m["roofline"]["kernel_ms"],
+                             "table_rows": m["config"]["table_rows"], "parity": m["parity"], "e2e": m["e2e"]["value"]})
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "workload": "c5 rule-table sweep (64 B flood, 100M packets/GPU)", "n_gpus": world, "unit": "Mpackets/s", "sweep": rows}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    main = measure(args, args.workload, full=True)
+    also = {}
+    for name in [x for x in args.also.split(",") if x and x != args.workload]:
+        m = measure(args, name, full=False)
+        if rank == 0:
+            also[name] = {k: m[k] for k in ("value", "unit", "ms_per_step", "roofline", "e2e", "parity", "gpu_launches")}
+            also[name]["workload"] = m["config"]["workload"]
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": main["value"], "unit": "Mpackets/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        }
+        line.update({k: v for k, v in main.items() if k not in ("value", "unit", "ms_per_step")})
+        if also:
+            line["also"] = also
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -417,12 +634,21 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", help="c2 | c2v6 | c3 | c3h | c4 | c5[:entries]   (default: c3, the north-star configuration)")
+    ap.add_argument("--also", default=None, help="comma-separated workloads measured in the same run and reported under \"also\" (default: c2 next to c3)")
+    ap.add_argument("--sweep", action="store_true", help="c5 rule-table sweep 2^4..2^20 entries: value and roofline fraction per size")
     ap.add_argument("--packets", type=int, default=0, help="override packets per GPU per step")
+    ap.add_argument("--seconds", type=float, default=3.0, help="length of the sustained leg (0 = skip)")
+    ap.add_argument("--ref-sample-seconds", type=float, default=2.0, help="length of one CPU sample of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--reserved-sms", type=int, default=-1, help="SMs the classify kernels leave to the side-stream collective (default: 4 when N > 1, else 0)")
     ap.add_argument("--metrics-capacity", type=int, default=131072, help="metrics_map max_entries per GPU (reference: 16384; the synthetic capture produces ~76k distinct keys)")
     args = ap.parse_args()
+    if args.workload not in WORKLOADS and not args.workload.startswith("c5:"):
+        ap.error(f"unknown workload {args.workload}")
+    if args.also is None:
+        args.also = "c2" if args.workload == "c3" else ""
     if args.impl == "reference":
         run_reference(args)
     else:

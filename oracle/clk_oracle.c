@@ -30,6 +30,7 @@
 #include <time.h>
 #include <stdio.h>
 #include <pthread.h>
+#include <sched.h>
 
 #include "../include/clawker_gpu.h"
 #include "hmap.h"
@@ -868,6 +869,63 @@ double orc_classify_batch_timed(const orc_tables *t, const uint8_t *pkts, const 
     for (int k = 0; k < nthreads; k++) pthread_join(th[k], NULL);
     clock_gettime(CLOCK_MONOTONIC, &b);
     for (int k = 0; k < nthreads; k++) if (js[k].j.mx) orc_metrics_free(js[k].j.mx);
+    pthread_barrier_destroy(&go); free(th); free(js);
+    return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+}
+
+/* Stabilised CPU-baseline form (bench.py): like orc_classify_batch_timed, plus
+ *   - each thread is pinned to one CPU of the process's affinity set (thread k -> k-th allowed CPU, wrapping),
+ *   - each thread works on a PRIVATE copy of its slice that it allocated and first-touched itself (so the pages sit on
+ *     its own NUMA node, as the socket buffers of a process running on that CPU would),
+ *   - the slice is classified `repeat` times inside the timed section, so a sample can be made seconds long.
+ * Verdicts of the last pass land in `verdicts`.  Returns seconds from release to the last thread done. */
+typedef struct tjob2 { job j; pthread_barrier_t *go; int cpu, repeat; uint8_t *own; uint32_t *own_offs; } tjob2;
+static void *tjob2_run(void *arg)
+{
+    tjob2 *tj = (tjob2 *)arg; job *j = &tj->j;
+    if (tj->cpu >= 0) { cpu_set_t cs; CPU_ZERO(&cs); CPU_SET(tj->cpu, &cs); pthread_setaffinity_np(pthread_self(), sizeof cs, &cs); }
+    /* private copy of the slice (first touch on this thread) */
+    const uint64_t cnt = j->hi - j->lo;
+    job local = *j;
+    if (cnt) {
+        if (j->offs16) {
+            const uint64_t b0 = (uint64_t)j->offs16[j->lo] * 16, b1 = (uint64_t)j->offs16[j->hi] * 16;
+            tj->own = malloc(b1 - b0 + 16); tj->own_offs = malloc((cnt + 1) * sizeof(uint32_t));
+            memcpy(tj->own, j->pkts + b0, b1 - b0);
+            for (uint64_t i = 0; i <= cnt; i++) tj->own_offs[i] = j->offs16[j->lo + i] - j->offs16[j->lo];
+            local.pkts = tj->own; local.offs16 = tj->own_offs;
+        } else {
+            tj->own = malloc(cnt * j->stride);
+            memcpy(tj->own, j->pkts + j->lo * j->stride, cnt * j->stride);
+            local.pkts = tj->own;
+        }
+        local.lo = 0; local.hi = cnt; local.verdicts = j->verdicts + j->lo;
+    }
+    pthread_barrier_wait(tj->go);
+    for (int r = 0; r < tj->repeat; r++) job_run(&local);
+    return NULL;
+}
+
+double orc_classify_batch_timed2(const orc_tables *t, const uint8_t *pkts, const uint32_t *offs16, uint32_t stride, uint64_t n,
+                                 uint32_t flags, uint32_t *verdicts, int nthreads, int repeat, int pin)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (repeat < 1) repeat = 1;
+    int cpus[4096], ncpu = 0;
+    if (pin) { cpu_set_t cs; CPU_ZERO(&cs); if (sched_getaffinity(0, sizeof cs, &cs) == 0) for (int c = 0; c < CPU_SETSIZE && ncpu < 4096; c++) if (CPU_ISSET(c, &cs)) cpus[ncpu++] = c; }
+    pthread_t *th = calloc(nthreads, sizeof *th); tjob2 *js = calloc(nthreads, sizeof *js);
+    pthread_barrier_t go; pthread_barrier_init(&go, NULL, (unsigned)nthreads + 1);
+    for (int k = 0; k < nthreads; k++) {
+        js[k].j = (job){ t, (flags & CLK_F_NO_METRICS) ? NULL : orc_metrics_new(), pkts, offs16, stride, n * k / nthreads, n * (k + 1) / nthreads, flags, verdicts };
+        js[k].go = &go; js[k].repeat = repeat; js[k].cpu = ncpu ? cpus[k % ncpu] : -1;
+        pthread_create(&th[k], NULL, tjob2_run, &js[k]);
+    }
+    struct timespec a, b;
+    pthread_barrier_wait(&go);
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    for (int k = 0; k < nthreads; k++) pthread_join(th[k], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    for (int k = 0; k < nthreads; k++) { if (js[k].j.mx) orc_metrics_free(js[k].j.mx); free(js[k].own); free(js[k].own_offs); }
     pthread_barrier_destroy(&go); free(th); free(js);
     return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
 }

@@ -82,6 +82,8 @@ class Oracle:
         L.orc_classify_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         L.orc_classify_batch_timed.restype = C.c_double
         L.orc_classify_batch_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int]
+        L.orc_classify_batch_timed2.restype = C.c_double
+        L.orc_classify_batch_timed2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_metrics_count.restype = C.c_uint32
         L.orc_metrics_count.argtypes = [C.c_void_p]
         L.orc_metrics_dump.restype = C.c_uint32
@@ -167,6 +169,22 @@ class Oracle:
             verd = np.zeros(n, dtype=np.uint32)
         assert verd.size >= n and verd.dtype == np.uint32
         return float(self.lib.orc_classify_batch_timed(self.t, pkts.ctypes.data, op, stride, n, flags, verd.ctypes.data, nthreads))
+
+    def classify_timed2(self, pkts: np.ndarray, offs16: np.ndarray | None = None, stride: int = 64, flags: int = 0,
+                        nthreads: int = 1, repeat: int = 1, pin: bool = True, verd: np.ndarray | None = None) -> float:
+        """Stabilised CPU-baseline form: threads pinned one per allowed CPU, every thread classifies a private,
+        self-allocated copy of its slice `repeat` times inside the timed section.  Seconds of the parallel section."""
+        pkts = np.ascontiguousarray(pkts, dtype=np.uint8)
+        if offs16 is None:
+            n, op = pkts.size // stride, None
+        else:
+            offs16 = np.ascontiguousarray(offs16, dtype=np.uint32)
+            n, op = offs16.size - 1, offs16.ctypes.data
+        if verd is None:
+            verd = np.zeros(n, dtype=np.uint32)
+        assert verd.size >= n and verd.dtype == np.uint32
+        return float(self.lib.orc_classify_batch_timed2(self.t, pkts.ctypes.data, op, stride, n, flags, verd.ctypes.data,
+                                                        nthreads, repeat, 1 if pin else 0))
 
     def classify_events(self, events: np.ndarray, flags: int = 0):
         events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)

@@ -67,14 +67,17 @@ def test_clock_sampler_falls_back_without_nvml(monkeypatch):
 
 
 def test_reference_arm_line():
-    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1", "--ref-sample-seconds", "0.2"],
                        capture_output=True, text=True, timeout=600, cwd=str(ROOT))
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "Mpackets/s" and d["value"] > 0
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
-    assert d["config"]["workload"] == bench.WORKLOADS["c2"]["desc"] and d["steps"] == 2 and d["warmup"] == 1
+    assert d["config"]["workload"] == bench.WORKLOADS["c3"]["desc"] and d["steps"] == 3 and d["warmup"] == 1        # the north-star configuration is the default
+    assert d["cpu_baseline"]["samples"] == 3 and d["cpu_baseline"]["min"] <= d["value"] <= d["cpu_baseline"]["max"]
+    assert set(d["config"]) == {"workload", "packets_per_gpu_per_step", "egress_rules", "table_rows", "layout", "synthetic", "l2_policy", "parallelism"}
+    assert d["config"]["packets_per_gpu_per_step"] == 100_000_000 and d["config"]["table_rows"]["domains"] == 10000
 
 
 def test_clock_sampler_never_armed_stops_cleanly():
@@ -129,6 +132,8 @@ class _FakeEngine:
     classify_slots_dev = classify_varlen_dev = totals_export = counters_export = _launch
 
     def counters_import(self, *a): pass
+    def counters_reset(self): pass
+    def close(self): pass
 
     def classify_slots(self, pk, stride, flags, out=None): pass
     def classify_varlen(self, pk, offs, flags, out=None): pass
@@ -173,7 +178,7 @@ def _dry_run(monkeypatch, capsys, world, workload):
     monkeypatch.setenv("RANK", "0")
     monkeypatch.setenv("LOCAL_RANK", "0")
     monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", str(world), "--steps", "4", "--warmup", "3", "--workload", workload,
-                                      "--packets", "8192", "--no-cpu-baseline"])
+                                      "--packets", "8192", "--no-cpu-baseline", "--no-parity", "--seconds", "0", "--also", ""])
     bench.main()
     return json.loads(capsys.readouterr().out.strip().splitlines()[-1])
 
@@ -190,6 +195,6 @@ def test_run_gpu_flow_single(monkeypatch, capsys):
 
 def test_run_gpu_flow_multi_and_varlen(monkeypatch, capsys):
     d = _dry_run(monkeypatch, capsys, 2, "c2")
-    assert d["n_gpus"] == 2 and d["gpu_launches"] == 8 and "4 SMs reserved" in d["config"]["parallelism"]     # classify + totals per step
+    assert d["n_gpus"] == 2 and d["gpu_launches"] == 8 and "4 SMs reserved" in d["config"]["collective"]     # classify + totals per step
     d = _dry_run(monkeypatch, capsys, 1, "c3h")
-    assert d["roofline"]["kernel"] == "clk::k_varlen_fast" and d["config"]["layout"].startswith("varlen")
+    assert d["roofline"]["kernel"].startswith("clk::k_varlen") and d["config"]["layout"].startswith("varlen")
