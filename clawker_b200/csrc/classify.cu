@@ -809,121 +809,218 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel 1b: variable-length captures with the name stage (BASELINE config 3)
+// kernel 1b: variable-length captures with the name stage (BASELINE config 3, the north-star workload)
 // ------------------------------------------------------------------------------------------------
-// Phase A (every packet, all lanes converged): the same predicated L3/L4 ladder as the slot kernel on the
-// first 40 header bytes, which also says what payload work is left (nm).  Packets that need payload work
-// are NOT parsed in place — byte-serial parsing with one lane active would dominate the kernel — they are
-// compacted into per-warp queues BY TYPE, and each queue is drained 32 packets at a time, so that all 32
-// lanes run the same parser (DNS question, TLS ClientHello, DNS answer, or the generic path for rare frames).
-#define VL_WARPS 16
-#define VL_QUEUES 6            // generic, dns query (udp), dns query (tcp), egress payload (tls), dns answer, http
-#define VL_QCAP 64
+// The frames of consecutive packets are contiguous in the blob, so a CTA stages the whole byte span of a CHUNK of
+// kThreads packets into shared memory with ONE bulk TMA copy (cp.async.bulk, double-buffered: the span of the next
+// chunk lands while this one is classified) and every byte the kernel looks at afterwards — header words and
+// payload parsers alike — is read from shared memory.  DRAM sees each frame exactly once.
+//
+// Phase A (one thread per packet, all lanes converged): the predicated L3/L4 ladder of the slot kernel on the
+// staged header words; it also says what payload work is left (nm).  Packets that need payload work are NOT parsed
+// in place — a byte-serial parser with a few lanes active would dominate the kernel — their thread indices are
+// compacted into per-type CTA lists.  Phase B: the lists are cut into 32-entry units which the warps of the CTA
+// share out, so a warp runs ONE parser (DNS question / DNS-over-TCP / ClientHello / DNS answer / HTTP request) with
+// its lanes full.  Frames the fast ladder does not cover (IPv6, IP options, runts) and chunks whose span exceeds the
+// stage (jumbo frames) are marked with CLK_W_REST in the verdict array and queued for k_varlen_rest, which runs the
+// generic path on them from global memory.
+#define VC_LISTS 5                  // NM_DNSQ .. NM_HTTP (list k-1 holds the threads whose packets need work k)
+#define CLK_W_REST 0xffffffffu      // not a verdict word (bits [1:0] == 3): "k_varlen_rest owes this packet"
 
-__device__ __forceinline__ void payload_window(const uint8_t *pk, uint32_t avail, bool tcp, uint32_t &po, uint32_t &pl)
+template <class P>
+__device__ __forceinline__ void payload_window(P pk, uint32_t avail, bool tcp, uint32_t &po, uint32_t &pl)
 {
     // simple IPv4 (ihl 5): l4off = 34; same arithmetic as name_stage()
-    uint32_t end = 14 + gbe16(pk + 16); if (end > avail) end = avail;
+    uint32_t end = 14 + gbe16(pk + 16u); if (end > avail) end = avail;
     po = 0; pl = 0;
     if (!tcp) { po = 42; if (po <= end) pl = end - po; }
-    else if (34 + 13 <= avail) { uint32_t doff = (gb(pk + 46) >> 4) * 4; po = 34 + doff; if (doff >= 20 && po <= end) pl = end - po; }
+    else if (34 + 13 <= avail) { uint32_t doff = (gb(pk + 46u) >> 4) * 4; po = 34 + doff; if (doff >= 20 && po <= end) pl = end - po; }
 }
 
-__device__ __noinline__ uint32_t name_work(const DevTables &T, const uint8_t *pk, uint32_t avail, uint32_t type, uint32_t word)
+// One unit of phase B: every lane of `mask` holds a packet of the SAME work type and calls together.
+template <class P>
+__device__ __noinline__ uint32_t name_work(const DevTables &T, P pk, uint32_t avail, uint32_t type, uint32_t word, unsigned mask)
 {
     uint32_t po, pl;
     if (type == NM_DNSA) {
-        uint32_t end = 14 + gbe16(pk + 16); if (end > avail) end = avail;
-        if (42 > end) return 0;
-        uint32_t nv, nupd = dns_answer_updates(T, pk + 42, end - 42, 0, nullptr, 0, 0, &nv);
-        return (nv << 4) | (nupd << 27);
+        uint32_t end = 14 + gbe16(pk + 16u); if (end > avail) end = avail;
+        const bool has = 42 <= end;
+        uint32_t nv, nupd = dns_answer_updates(T, pk + 42u, has ? end - 42 : 0u, 0, nullptr, 0, 0, &nv, mask);
+        return has ? (nv << 4) | (nupd << 27) : 0u;
     }
     payload_window(pk, avail, type != NM_DNSQ, po, pl);
     uint32_t name = CLK_N_NA;
-    if (type == NM_DNSQ) name = dns_query_verdict(T, pk + po, pl);
-    else if (type == NM_DNSQ_TCP) { if (pl > 0) name = (pl >= 2 && gbe16(pk + po) + 2 <= pl) ? dns_query_verdict(T, pk + po + 2, gbe16(pk + po)) : CLK_N_DENY; }
+    if (type == NM_DNSQ) name = dns_query_verdict(T, pk + po, pl, mask);
+    else if (type == NM_DNSQ_TCP) {
+        const bool framed = pl >= 2 && gbe16(pk + po) + 2 <= pl;
+        const uint32_t v = dns_query_verdict(T, pk + (po + 2), framed ? gbe16(pk + po) : 0u, mask);
+        if (pl > 0) name = framed ? v : CLK_N_DENY;
+    }
     else if (type == NM_HTTP) { if (pl > 0) name = http_host_verdict(T, pk + po, pl); }
-    else if (pl > 0) name = egress_payload_verdict(T, pk + po, pl);
+    else { const uint32_t v = tls_sni_verdict(T, pk + po, pl, mask); if (pl > 0) name = v; }
     return word | (name << 4);
 }
 
-__global__ void __launch_bounds__(VL_WARPS * 32, 2) k_varlen_fast(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts,
-                                                                  const uint32_t *__restrict__ offs16, unsigned long long n,
-                                                                  uint32_t flags, uint32_t *__restrict__ verdicts)
+struct VcMeta { uint32_t pkoff, words, lists, cnt, total; };
+__host__ __device__ inline VcMeta vc_meta(uint32_t threads)
+{
+    VcMeta M; uint32_t o = 0;
+    M.pkoff = o; o += threads * 4;                 // per packet: span offset (16 B units) | captured length (16 B units) << 16
+    M.words = o; o += threads * 4;                 // phase-A verdict word
+    M.lists = o; o += VC_LISTS * threads * 2;      // u16 thread indices per work type
+    M.cnt = o; o += 2 * 8 * 4;                     // list lengths, double-buffered by chunk parity
+    M.total = (o + 15u) & ~15u;
+    return M;
+}
+
+// rest_q: [0] entries appended, [1] overflow flag, [2..2+rest_cap) packet indices
+template <int kThreads, int kCap, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_varlen_chunk(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts,
+                                                                      const uint32_t *__restrict__ offs16, uint32_t n, uint32_t flags,
+                                                                      uint32_t *__restrict__ verdicts, uint32_t *__restrict__ rest_q, uint32_t rest_cap)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemLayout L = smem_layout(T, 0, VL_WARPS * VL_QUEUES * VL_QCAP * 8, 0, MSLOTS, VL_WARPS);
+    constexpr uint32_t kWarps = kThreads / 32;
+    const VcMeta M = vc_meta(kThreads);
+    const SmemLayout L = smem_layout(T, 2 * kCap, M.total, 2, MSLOTS, kWarps);
     Tabs tb; MetricAgg ag;
-    cta_prologue<false>(T, smem, L, 0, tb, ag);
-    __syncthreads();
+    cta_prologue<false>(T, smem, L, 2, tb, ag);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint2 *queue = (uint2 *)(smem + L.queue) + warp * (VL_QUEUES * VL_QCAP);      // entry: {packet index, phase-A word}
-    const uint32_t n32 = (uint32_t)n, n_tiles = (n32 + 31u) >> 5;
-    const uint32_t gw = blockIdx.x * VL_WARPS + warp, W = gridDim.x * VL_WARPS;
+    uint64_t *bars = (uint64_t *)(smem + L.bars);
+    uint8_t *bufs = smem + L.tiles;
+    uint32_t *pkoff = (uint32_t *)(smem + L.queue + M.pkoff), *words = (uint32_t *)(smem + L.queue + M.words);
+    uint16_t *lists = (uint16_t *)(smem + L.queue + M.lists);
+    uint32_t *cnt = (uint32_t *)(smem + L.queue + M.cnt);
+    if (tid < 16) cnt[tid] = 0;
+    const uint32_t n_chunks = (n + kThreads - 1) / kThreads;
     const bool do_metrics = !(flags & CLK_F_NO_METRICS);
-    uint32_t qn[VL_QUEUES];
-    #pragma unroll
-    for (int k = 0; k < VL_QUEUES; k++) qn[k] = 0;
+    __syncthreads();                                        // tables staged, aggregation table and counters zeroed, barriers initialised
 
-    // drain up to 32 entries of queue k, every participating lane running the same parser
-    auto drain = [&](int k, uint32_t take) {
-        uint2 ent = make_uint2(0, 0);
-        if (lane < take) ent = queue[k * VL_QCAP + lane];
-        const uint2 carry = (lane + 32 < qn[k]) ? queue[k * VL_QCAP + lane + 32] : make_uint2(0, 0);
-        bool hm = false, defer = false; unsigned long long mk = 0;
-        const bool split = k == (int)NM_TLS && T.n_http != 0;              // plaintext HTTP shares the egress port with TLS
-        if (lane < take) {
-            const uint32_t o0 = __ldg(&offs16[ent.x]), o1 = __ldg(&offs16[ent.x + 1]);
-            const uint8_t *pk = pkts + (unsigned long long)o0 * 16ull; const uint32_t avail = (o1 - o0) * 16u;
-            if (split) { uint32_t po, pl; payload_window(pk, avail, true, po, pl); defer = pl >= 1 && gb(pk + po) != 0x16u; }
-            if (!defer) {
-                uint32_t w = k == 0 ? generic_one(T, tb, pk, avail, flags, hm, mk) : name_work(T, pk, avail, (uint32_t)k, ent.y);
-                stg_stream(&verdicts[ent.x], w);
-            }
+    // thread 0: start the bulk copy of chunk c into stage s (nothing is copied for an empty or oversize span)
+    auto issue = [&](uint32_t c, uint32_t s) {
+        if (c >= n_chunks) return;
+        const uint32_t lo = c * kThreads, hi = (n - lo < (uint32_t)kThreads) ? n : lo + kThreads;
+        const uint32_t o_lo = __ldg(&offs16[lo]), units = __ldg(&offs16[hi]) - o_lo;
+        if (units != 0 && units <= kCap / 16) {
+            mbar_expect_tx(&bars[s], units * 16);
+            tma_load_1d(bufs + s * kCap, pkts + (unsigned long long)o_lo * 16ull, units * 16, &bars[s]);
         }
-        if (split) {                                                       // requests wait for a full warp of their own
-            const unsigned dm = __ballot_sync(0xffffffffu, defer);
-            if (defer) queue[NM_HTTP * VL_QCAP + qn[NM_HTTP] + __popc(dm & ((1u << lane) - 1u))] = ent;
-            qn[NM_HTTP] += __popc(dm);
-        }
-        if (k == 0 && do_metrics) metric_warp_emit(T, ag, hm, mk);
-        __syncwarp();
-        if (lane + 32 < qn[k]) queue[k * VL_QCAP + lane] = carry;
-        qn[k] -= take;
-        __syncwarp();
     };
+    if (tid == 0) { issue(blockIdx.x, 0); issue(blockIdx.x + gridDim.x, 1); }
 
-    for (uint32_t t = gw; t < n_tiles; t += W) {
-        const uint32_t i = (t << 5) + lane;
-        bool hm = false; unsigned long long mk = 0; uint32_t w = 0, kind = 0xffu;   // kind: queue to join, 0xff = done in phase A
-        if (i < n32) {
-            const uint32_t o0 = __ldg(&offs16[i]), o1 = __ldg(&offs16[i + 1]);
-            const uint8_t *pk = pkts + (unsigned long long)o0 * 16ull; const uint32_t avail = (o1 - o0) * 16u;
-            kind = 0;
-            if (avail >= 64) {
-                const uint32_t w3 = __ldg((const uint32_t *)(pk + 12));
-                const uint4 q1 = __ldg((const uint4 *)(pk + 16));
-                const uint4 q2 = __ldg((const uint4 *)(pk + 32));
+    uint32_t it = 0, uses0 = 0, uses1 = 0;                  // completed copies per stage (an unstaged chunk does not flip its barrier)
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x, it++) {
+        const uint32_t s = it & 1u;
+        const uint32_t lo = c * kThreads, hi = (n - lo < (uint32_t)kThreads) ? n : lo + kThreads, i = lo + tid;
+        const bool valid = i < hi;
+        const uint32_t o_lo = __ldg(&offs16[lo]), units = __ldg(&offs16[hi]) - o_lo;
+        const uint32_t o0 = valid ? __ldg(&offs16[i]) : 0u, o1 = valid ? __ldg(&offs16[i + 1]) : 0u;
+        const bool staged = units != 0 && units <= kCap / 16;
+        uint32_t *cur = cnt + s * 8;
+        if (staged) { mbar_wait(&bars[s], (s ? uses1 : uses0) & 1u); if (s) uses1++; else uses0++; }
+        const uint8_t *buf = bufs + s * kCap;
+
+        // ---- phase A -------------------------------------------------------------------------------------------------
+        bool hm = false; unsigned long long mk = 0; uint32_t w = 0, kind = 0;          // kind: 0 done, 1..5 name work, 6 rest
+        if (valid) {
+            const uint32_t avail = (o1 - o0) * 16u;
+            kind = 6;
+            if (staged && avail >= 64) {
+                const uint8_t *b = buf + (o0 - o_lo) * 16u;
+                const uint32_t w3 = *(const uint32_t *)(b + 12);
+                const uint4 q1 = *(const uint4 *)(b + 16);
+                const uint4 q2 = *(const uint4 *)(b + 32);
                 uint32_t nm;
-                if (fast_classify<true>(T, tb, w3, q1, q2.x, q2.y, q2.w, avail, flags, w, hm, mk, nm)) kind = nm == NM_NONE ? 0xffu : nm;
+                if (fast_classify<true>(T, tb, w3, q1, q2.x, q2.y, q2.w, avail, flags, w, hm, mk, nm)) {
+                    kind = nm;
+                    if (nm == NM_TLS && T.n_http) {                                     // plaintext HTTP shares the egress port with TLS
+                        const uint32_t po = 34 + ((q2.w >> 20) & 0xfu) * 4;              // < end <= avail (fast_classify checked)
+                        if (b[po] != 0x16u) kind = NM_HTTP;
+                    }
+                    if (nm != NM_NONE) { pkoff[tid] = (o0 - o_lo) | ((o1 - o0) << 16); words[tid] = w; }
+                }
             }
-            if (kind == 0xffu) stg_stream(&verdicts[i], w);
+            if (kind == 0) stg_stream(&verdicts[i], w);
+            else if (kind == 6) stg_stream(&verdicts[i], CLK_W_REST);
         }
         if (do_metrics) metric_warp_emit(T, ag, hm, mk);
         #pragma unroll
-        for (int k = 0; k < VL_QUEUES; k++) {
-            const unsigned m = __ballot_sync(0xffffffffu, kind == (uint32_t)k);
+        for (uint32_t k = 1; k <= VC_LISTS; k++) {
+            const unsigned m = __ballot_sync(0xffffffffu, kind == k);
             if (m) {
-                if (kind == (uint32_t)k) queue[k * VL_QCAP + qn[k] + __popc(m & ((1u << lane) - 1u))] = make_uint2(i, w);
-                qn[k] += __popc(m);
-                __syncwarp();
-                if (qn[k] >= 32) drain(k, 32);
-                if (k == (int)NM_TLS && qn[NM_HTTP] >= 32) drain((int)NM_HTTP, 32);
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cur[k], (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (kind == k) lists[(k - 1) * kThreads + base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)tid;
             }
         }
+        {
+            const unsigned m = __ballot_sync(0xffffffffu, kind == 6);
+            if (m) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&rest_q[0], (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (kind == 6) {
+                    const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (pos < rest_cap) rest_q[2 + pos] = i; else rest_q[1] = 1u;
+                }
+            }
+        }
+        __syncthreads();                                    // lists complete
+        if (tid < 8) cnt[(s ^ 1u) * 8 + tid] = 0;            // the other parity's counters: last read before the previous chunk's final barrier
+
+        // ---- phase B: 32-entry units of the lists, shared out over the warps ----------------------------------------
+        {
+            uint32_t u = 0;
+            #pragma unroll 1
+            for (uint32_t k = 1; k <= VC_LISTS; k++) {
+                const uint32_t len = cur[k];
+                #pragma unroll 1
+                for (uint32_t e0 = 0; e0 < len; e0 += 32, u++) {
+                    if (u % kWarps != warp) continue;
+                    const uint32_t e = e0 + lane;
+                    const unsigned um = __ballot_sync(0xffffffffu, e < len);          // the unit's lanes (the loop is warp-uniform)
+                    if (e < len) {
+                        const uint32_t t = lists[(k - 1) * kThreads + e], po = pkoff[t];
+                        const SP pk = SP{ smem_u32(buf) + (po & 0xffffu) * 16u };
+                        stg_stream(&verdicts[lo + t], name_work(T, pk, (po >> 16) * 16u, k, words[t], um));
+                    }
+                }
+            }
+        }
+        __syncthreads();                                    // every reader of this stage is done
+        if (tid == 0) { fence_proxy_async(); issue(c + 2 * gridDim.x, s); }
     }
-    #pragma unroll
-    for (int k = 0; k < VL_QUEUES; k++) while (qn[k]) drain(k, qn[k] < 32 ? qn[k] : 32);   // NM_HTTP last: draining NM_TLS feeds it
+    if (do_metrics) metric_cta_flush(T, ag);
+}
+
+// The packets k_varlen_chunk left behind (CLK_W_REST): the generic path, straight from global memory.
+__global__ void __launch_bounds__(256) k_varlen_rest(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts,
+                                                     const uint32_t *__restrict__ offs16, uint32_t n, uint32_t flags,
+                                                     uint32_t *__restrict__ verdicts, const uint32_t *__restrict__ rest_q, uint32_t rest_cap)
+{
+    const uint32_t cnt = rest_q[0], overflow = rest_q[1];
+    if (cnt == 0) return;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
+    Tabs tb; MetricAgg ag;
+    cta_prologue<false>(T, smem, L, 0, tb, ag);
+    __syncthreads();
+    const bool do_metrics = !(flags & CLK_F_NO_METRICS);
+    const uint32_t step = gridDim.x * blockDim.x, g = blockIdx.x * blockDim.x + threadIdx.x;
+    // queue overflow (more leftovers than the queue holds): find them by their mark instead
+    const uint32_t total = overflow ? n : (cnt < rest_cap ? cnt : rest_cap), total_round = (total + 31u) & ~31u;
+    for (uint32_t k = g; k < total_round; k += step) {
+        bool hm = false; unsigned long long mk = 0;
+        if (k < total) {
+            const uint32_t j = overflow ? k : rest_q[2 + k];
+            if (!overflow || verdicts[j] == CLK_W_REST) {
+                const uint32_t o0 = __ldg(&offs16[j]), o1 = __ldg(&offs16[j + 1]);
+                stg_stream(&verdicts[j], generic_one(T, tb, pkts + (unsigned long long)o0 * 16ull, (o1 - o0) * 16u, flags, hm, mk));
+            }
+        }
+        if (do_metrics) metric_warp_emit(T, ag, hm, mk);
+    }
     if (do_metrics) metric_cta_flush(T, ag);
 }
 
@@ -1239,19 +1336,46 @@ const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride
 #undef FAST_ARGS
 }
 
+template <int kThreads, int kCap, int kMinBlocks>
+static const char *launch_chunk(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, uint32_t n, uint32_t flags,
+                                uint32_t *d_verdicts, cudaStream_t st, uint32_t *rest_q, uint32_t rest_cap, LaunchInfo *info)
+{
+    int grid = 0; cudaError_t e;
+    const SmemLayout L = smem_layout(T, 2 * kCap, vc_meta(kThreads).total, 2, MSLOTS, kThreads / 32);
+    if ((e = occupancy_grid(T, k_varlen_chunk<kThreads, kCap, kMinBlocks>, kThreads, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
+    const uint32_t need = (n + kThreads - 1) / kThreads; if ((uint32_t)grid > need) grid = (int)need;
+    if ((e = cudaMemsetAsync(rest_q, 0, 8, st)) != cudaSuccess) return cudaGetErrorString(e);
+    k_varlen_chunk<kThreads, kCap, kMinBlocks><<<grid, kThreads, L.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, n, flags, d_verdicts, rest_q, rest_cap);
+    if (info) { info->grid = grid; info->block = kThreads; info->smem = L.total; info->launches = 2; }
+    if ((e = cudaGetLastError()) != cudaSuccess) return cudaGetErrorString(e);
+    const SmemLayout R = smem_layout(T, 0, 0, 0, MSLOTS, 8);
+    int rgrid = 0;
+    if ((e = occupancy_grid(T, k_varlen_rest, 256, R.total, &rgrid)) != cudaSuccess) return cudaGetErrorString(e);
+    if ((uint32_t)rgrid > (n + 255) / 256) rgrid = (int)((n + 255) / 256);
+    k_varlen_rest<<<rgrid, 256, R.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, n, flags, d_verdicts, rest_q, rest_cap);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+uint32_t varlen_rest_cap(unsigned long long n) { return (uint32_t)(n / 8 + 65536); }
+
+// rest_q: device scratch of (2 + varlen_rest_cap(n)) words owned by this launch (the engine keeps one per stream)
 const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n, uint32_t flags,
-                          uint32_t *d_verdicts, cudaStream_t st, LaunchInfo *info)
+                          uint32_t *d_verdicts, cudaStream_t st, uint32_t *rest_q, LaunchInfo *info)
 {
     if (n == 0) return nullptr;
     int grid = 0; cudaError_t e;
-    if (n < 0x7fffffffull && !getenv("CLK_VARLEN_GENERIC")) {
-        SmemLayout L = smem_layout(T, 0, VL_WARPS * VL_QUEUES * VL_QCAP * 8, 0, MSLOTS, VL_WARPS);
-        if ((e = occupancy_grid(T, k_varlen_fast, VL_WARPS * 32, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
-        unsigned long long need = ((n + 31) / 32 + VL_WARPS - 1) / VL_WARPS; if ((unsigned long long)grid > need) grid = (int)need;
-        k_varlen_fast<<<grid, VL_WARPS * 32, L.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, n, flags, d_verdicts);
-        if (info) { info->grid = grid; info->block = VL_WARPS * 32; info->smem = L.total; }
-        e = cudaGetLastError();
-        return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+    if (n < 0x7fffffffull && rest_q && !getenv("CLK_VARLEN_GENERIC")) {
+        const uint32_t cap = varlen_rest_cap(n);
+        int cfg = 0; if (const char *s = getenv("CLK_VC")) cfg = atoi(s);
+#define VC_ARGS T, d_pkts, d_offs16, (uint32_t)n, flags, d_verdicts, st, rest_q, cap, info
+        switch (cfg) {
+        case 1:  return launch_chunk<256, 36 * 1024, 2>(VC_ARGS);
+        case 2:  return launch_chunk<128, 20 * 1024, 4>(VC_ARGS);
+        case 3:  return launch_chunk<512, 72 * 1024, 1>(VC_ARGS);
+        default: return launch_chunk<192, 28 * 1024, 3>(VC_ARGS);
+        }
+#undef VC_ARGS
     }
     SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
     if ((e = occupancy_grid(T, k_generic<true>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);

@@ -94,7 +94,9 @@ struct clk_engine {
     DevBuf m_keys, m_counts, m_dropped;      // this GPU's metrics_map (kernels write)
     DevBuf g_keys, g_counts, g_dropped;      // merged view after the all-gather (clk_counters_import)
     uint32_t g_mask = 0;                       // its slot mask: sized for n_blocks full tables at load <= 1/2
-    DevBuf work_rare[4];                       // rare-frame queues: [0..2] host pipeline lanes, [3] the *_dev entry
+    DevBuf work_rare[3];                       // rare / leftover-frame queues of the host pipeline lanes
+    std::map<cudaStream_t, DevBuf> scratch;    // the same for the *_dev entries: one per caller stream, so launches in flight on
+                                               // different streams of one engine never share a queue
     DevBuf work_pkts[3], work_offs[3], work_verd[3], scan_sums, scan_pos, scan_total, upd_out, ctr_block;
     clk_stats stats;
     int loader = LOADER_TMA_SW64;
@@ -149,7 +151,7 @@ uint64_t name_key_of(const std::string &s)
 void build_name_table(const std::vector<std::string> &names, const std::vector<uint32_t> &vals, std::vector<NameSlot> &slots,
                       std::vector<uint8_t> &blob)
 {
-    uint32_t cap = pow2_at_least((uint64_t)names.size() * 2 + 1);
+    uint32_t cap = pow2_at_least((uint64_t)names.size() * 4 + 2);          // load <= 1/4, even home slots (dev_tables.h name_home)
     slots.assign(cap, NameSlot{ 0, 0, 0 });
     for (size_t i = 0; i < names.size(); i++) {
         const std::string &s = names[i];
@@ -158,7 +160,7 @@ void build_name_table(const std::vector<std::string> &names, const std::vector<u
         blob.push_back((uint8_t)s.size());
         for (unsigned char c : s) blob.push_back((c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c);
         uint64_t key = name_key_of(s);
-        uint32_t h = mix64(key) & (cap - 1);
+        uint32_t h = name_home(key, cap - 1);
         while (slots[h].key) h = (h + 1) & (cap - 1);
         slots[h] = NameSlot{ key, vals[i], off };
     }
@@ -402,6 +404,8 @@ int publish_locked(clk_engine *e)
     if (n_cidr) { T.cidr_pre = (const uint32_t *)S.cidr_pre.p; T.cidr_l1 = (const uint32_t *)S.cidr_l1.p; T.cidr_l2_keys = (const uint32_t *)S.cidr_l2_keys.p; T.cidr_l2_bits = (const uint32_t *)S.cidr_l2_bits.p; T.cidr_l2_mask = (uint32_t)l2_keys.size() - 1; T.cidr_l2_shift = shift_for((uint32_t)l2_keys.size()); }
     if (!zone_slots.empty()) { T.zone_slots = (const NameSlot *)S.zone.p; T.zone_mask = (uint32_t)zone_slots.size() - 1; }
     if (!sni_slots.empty()) { T.sni_slots = (const NameSlot *)S.sni.p; T.sni_mask = (uint32_t)sni_slots.size() - 1; }
+    for (auto &z : e->compiled.zones) T.zone_max_labels = std::max<uint32_t>(T.zone_max_labels, 1u + (uint32_t)std::count(z.begin(), z.end(), '.'));
+    for (auto &z : e->compiled.snis) if (!z.empty() && z[0] == '.') T.sni_max_dots = std::max<uint32_t>(T.sni_max_dots, (uint32_t)std::count(z.begin(), z.end(), '.'));
     T.names = (const uint8_t *)S.names.p;
     if (!http_vh.empty()) {
         T.n_http = (uint32_t)http_vh.size(); T.http_vh = (const uint32_t *)S.http_vh.p;
@@ -508,7 +512,8 @@ void clk_engine_destroy(clk_engine *e)
         cudaDeviceSynchronize();
         e->snap[0].release(); e->snap[1].release();
         for (DevBuf *b : { &e->m_keys, &e->m_counts, &e->m_dropped, &e->g_keys, &e->g_counts, &e->g_dropped, &e->scan_sums, &e->scan_pos, &e->scan_total, &e->upd_out, &e->ctr_block }) b->release();
-        for (int i = 0; i < 4; i++) e->work_rare[i].release();
+        for (int i = 0; i < 3; i++) e->work_rare[i].release();
+        for (auto &kv : e->scratch) kv.second.release();
         for (int i = 0; i < 3; i++) { e->work_pkts[i].release(); e->work_offs[i].release(); e->work_verd[i].release(); if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]); }
         if (e->ev0) cudaEventDestroy(e->ev0);
         if (e->ev1) cudaEventDestroy(e->ev1);
@@ -721,7 +726,7 @@ int clk_publish(clk_engine *e)
 static int finish_launch(clk_engine *e, const char *err, const LaunchInfo &li)
 {
     if (err) return fail(e, CLK_EIO, "kernel launch failed: %s", err);
-    e->stats.kernel_launches++; e->stats.last_grid = li.grid; e->stats.last_block = li.block; e->stats.last_smem_bytes = li.smem;
+    e->stats.kernel_launches += li.launches ? li.launches : 1; e->stats.last_grid = li.grid; e->stats.last_block = li.block; e->stats.last_smem_bytes = li.smem;
     return CLK_OK;
 }
 
@@ -733,11 +738,12 @@ int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, u
     std::lock_guard<std::mutex> g(e->mu);
     int rc = ensure_published(e); if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    LaunchInfo li = { 0, 0, 0 };
+    LaunchInfo li = { 0, 0, 0, 0 };
     if (!stream) cudaEventRecord(e->ev0, st);                 // a caller that brings its own stream brings its own events
-    CUDA_TRY(e, e->work_rare[3].ensure((n + (1u << 20)) * 4)); // per-CTA regions (packets of the CTA's tiles); grows only for larger batches
+    DevBuf &sc = e->scratch[st];                              // per stream: launches on one stream are ordered, others get their own
+    CUDA_TRY(e, sc.ensure((n + (1u << 20)) * 4));              // per-CTA regions (packets of the CTA's tiles); grows only for larger batches
     const char *err = launch_slots(e->T, d_pkts, stride, n, flags, (uint32_t *)d_verdicts, st, e->loader, e->stages,
-                                   (uint32_t *)e->work_rare[3].p + 2, (uint32_t *)e->work_rare[3].p, &li);
+                                   (uint32_t *)sc.p + 2, (uint32_t *)sc.p, &li);
     if (!stream) cudaEventRecord(e->ev1, st);
     return finish_launch(e, err, li);
 }
@@ -749,9 +755,11 @@ int clk_classify_varlen_dev(clk_engine *e, const void *d_pkts, const void *d_off
     std::lock_guard<std::mutex> g(e->mu);
     int rc = ensure_published(e); if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    LaunchInfo li = { 0, 0, 0 };
+    LaunchInfo li = { 0, 0, 0, 0 };
     if (!stream) cudaEventRecord(e->ev0, st);                 // a caller that brings its own stream brings its own events
-    const char *err = launch_varlen(e->T, d_pkts, (const uint32_t *)d_offs16, n, flags, (uint32_t *)d_verdicts, st, &li);
+    DevBuf &sc = e->scratch[st];
+    CUDA_TRY(e, sc.ensure(((size_t)varlen_rest_cap(n) + 2) * 4));
+    const char *err = launch_varlen(e->T, d_pkts, (const uint32_t *)d_offs16, n, flags, (uint32_t *)d_verdicts, st, (uint32_t *)sc.p, &li);
     if (!stream) cudaEventRecord(e->ev1, st);
     return finish_launch(e, err, li);
 }
@@ -776,7 +784,7 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
         }
         int s = k % 3; cudaStream_t st = e->pipe[s];
         CUDA_TRY(e, cudaStreamSynchronize(st));            // buffers of this lane are free again
-        LaunchInfo li = { 0, 0, 0 }; const char *err;
+        LaunchInfo li = { 0, 0, 0, 0 }; const char *err;
         CUDA_TRY(e, e->work_verd[s].ensure(cnt * 4));
         if (offs16) {
             uint64_t b0 = (uint64_t)offs16[done] * 16, b1 = (uint64_t)offs16[done + cnt] * 16;
@@ -786,7 +794,9 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
             CUDA_TRY(e, cudaMemcpyAsync(e->work_offs[s].p, offs16 + done, (cnt + 1) * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + b0, b1 - b0, cudaMemcpyHostToDevice, st));
             // offsets stay absolute: bias the base pointer instead of rewriting them
-            err = launch_varlen(e->T, (const uint8_t *)e->work_pkts[s].p - b0, (const uint32_t *)e->work_offs[s].p, cnt, flags, (uint32_t *)e->work_verd[s].p, st, &li);
+            CUDA_TRY(e, e->work_rare[s].ensure(((size_t)varlen_rest_cap(cnt) + 2) * 4));
+            err = launch_varlen(e->T, (const uint8_t *)e->work_pkts[s].p - b0, (const uint32_t *)e->work_offs[s].p, cnt, flags, (uint32_t *)e->work_verd[s].p, st,
+                                (uint32_t *)e->work_rare[s].p, &li);
         } else {
             CUDA_TRY(e, e->work_pkts[s].ensure(cnt * stride));
             CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + done * stride, cnt * stride, cudaMemcpyHostToDevice, st));
@@ -827,7 +837,7 @@ int clk_classify_events(clk_engine *e, const clk_event *events, uint64_t n, uint
     CUDA_TRY(e, e->work_pkts[0].ensure(n * sizeof(clk_event)));
     CUDA_TRY(e, e->work_verd[0].ensure(n * 4));
     CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[0].p, events, n * sizeof(clk_event), cudaMemcpyHostToDevice, st));
-    LaunchInfo li = { 0, 0, 0 };
+    LaunchInfo li = { 0, 0, 0, 0 };
     const char *err = launch_events(e->T, (const clk_event *)e->work_pkts[0].p, n, flags, (uint32_t *)e->work_verd[0].p, st, &li);
     rc = finish_launch(e, err, li); if (rc) return rc;
     CUDA_TRY(e, cudaMemcpyAsync(verdicts, e->work_verd[0].p, n * 4, cudaMemcpyDeviceToHost, st));

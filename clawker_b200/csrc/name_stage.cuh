@@ -6,19 +6,31 @@
 //                                                   matcher: Envoy v1.37 filter-chain server_names lookup)
 //   DNS answers   -> dns_cache update stream      (internal/dnsbpf/dnsbpf.go:75-97)
 //
-// Names are matched by a 64-bit polynomial suffix hash (one forward pass gives every label
-// suffix) against open-addressing tables, and every hash hit is confirmed byte-for-byte
-// against the stored name, so results equal an exact string-keyed map lookup.
+// Names are matched by a 64-bit polynomial suffix hash (one pass gives every label suffix) against
+// open-addressing tables, and every hash hit is confirmed byte-for-byte against the stored name, so
+// results equal an exact string-keyed map lookup.
+//
+// Every parser is a template over the payload pointer type P:
+//   const uint8_t *  — the frame in global memory (read through ld.global.nc; generic / rare-frame kernels)
+//   SP               — the frame in SHARED memory (a 32-bit shared-window address; the chunk kernel stages
+//                      whole spans of frames with one bulk TMA copy and parses them from there)
+// Table pointers (zones, server_names, names blob) are always global (L2-resident).
 
+struct SP { uint32_t a; };
+__device__ __forceinline__ SP operator+(SP p, uint32_t o) { return SP{ p.a + o }; }
+__device__ __forceinline__ SP operator-(SP p, uint32_t o) { return SP{ p.a - o }; }
+// volatile: never moved across the mbarrier wait that publishes the staged bytes (also volatile asm)
+__device__ __forceinline__ uint32_t gb(SP p) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(p.a)); return v; }
 __device__ __forceinline__ uint32_t gb(const uint8_t *p) { return __ldg(p); }
-__device__ __forceinline__ uint32_t gbe16(const uint8_t *p) { return (gb(p) << 8) | gb(p + 1); }
+template <class P> __device__ __forceinline__ uint32_t gbe16(P p) { return (gb(p) << 8) | gb(p + 1u); }
 __device__ __forceinline__ uint32_t lower(uint32_t c) { return (c - 'A' < 26u) ? c + 32u : c; }
 __device__ __forceinline__ bool zone_char(uint32_t c) { return (c - 'a' < 26u) || (c - '0' < 10u) || c == '_' || c == '-'; }
 
 // ---- DNS name walker (RFC 1035 §4.1.4; limits of miekg/dns UnpackDomainName: 255 octets, 126 pointers) -----
+template <class P>
 struct NameWalk {
-    const uint8_t *m; uint32_t mlen, p, wire, after; int ptrs; bool jumped;
-    __device__ __forceinline__ void init(const uint8_t *m_, uint32_t mlen_, uint32_t off) { m = m_; mlen = mlen_; p = off; wire = 0; after = off; ptrs = 0; jumped = false; }
+    P m; uint32_t mlen, p, wire, after; int ptrs; bool jumped;
+    __device__ __forceinline__ void init(P m_, uint32_t mlen_, uint32_t off) { m = m_; mlen = mlen_; p = off; wire = 0; after = off; ptrs = 0; jumped = false; }
     // Returns label length (>0) with p at its first byte, 0 at the root label, -1 if malformed.
     __device__ __forceinline__ int next_label()
     {
@@ -29,7 +41,7 @@ struct NameWalk {
                 if (p + 1 >= mlen) return -1;
                 if (!jumped) { after = p + 2; jumped = true; }
                 if (++ptrs > 126) return -1;
-                p = ((c & 0x3Fu) << 8) | gb(m + p + 1);
+                p = ((c & 0x3Fu) << 8) | gb(m + (p + 1));
                 continue;
             }
             if (c & 0xC0u) return -1;
@@ -44,7 +56,7 @@ struct NameWalk {
 
 __device__ __forceinline__ bool name_table_find(const NameSlot *slots, uint32_t mask, uint64_t key, uint32_t &h, NameSlot &out)
 {
-    // continues probing from h; caller initialises h = mix64(key) & mask
+    // continues probing from h; caller initialises h = name_home(key, mask)
     for (;;) {
         NameSlot s = slots[h];
         h = (h + 1) & mask;
@@ -53,15 +65,40 @@ __device__ __forceinline__ bool name_table_find(const NameSlot *slots, uint32_t 
     }
 }
 
-// Confirm that the label sequence starting at wire offset `lab` (pointing at a length byte) spells `str`.
-__device__ __forceinline__ bool dns_name_equals(const uint8_t *m, uint32_t mlen, uint32_t lab, const uint8_t *str, uint32_t slen)
+// One-load form: the aligned slot pair at the key's home decides unless both slots hold other keys.
+// Returns 1 hit (out), 0 miss, 2 undecided (continue with name_table_find from home + 2).
+struct NamePair { uint4 a, b; };
+__device__ __forceinline__ NamePair name_pair_load(const NameSlot *slots, uint32_t mask, uint64_t key)
 {
-    NameWalk w; w.init(m, mlen, lab);
+    const uint4 *p = (const uint4 *)(slots + name_home(key, mask));
+    NamePair r; r.a = __ldg(p); r.b = __ldg(p + 1);
+    return r;
+}
+__device__ __forceinline__ int name_pair_decide(const NamePair &pr, uint64_t key, NameSlot &out)
+{
+    const uint64_t k0 = ((uint64_t)pr.a.y << 32) | pr.a.x, k1 = ((uint64_t)pr.b.y << 32) | pr.b.x;
+    if (k0 == key) { out.key = k0; out.val = pr.a.z; out.str_off = pr.a.w; return 1; }
+    if (k0 == 0) return 0;
+    if (k1 == key) { out.key = k1; out.val = pr.b.z; out.str_off = pr.b.w; return 1; }
+    if (k1 == 0) return 0;
+    return 2;
+}
+__device__ __noinline__ bool name_table_find_from(const NameSlot *slots, uint32_t mask, uint64_t key, uint32_t skip, NameSlot &out)
+{
+    uint32_t h = (name_home(key, mask) + skip) & mask;
+    return name_table_find(slots, mask, key, h, out);
+}
+
+// Confirm that the label sequence starting at wire offset `lab` (pointing at a length byte) spells `str`.
+template <class P>
+__device__ __forceinline__ bool dns_name_equals(P m, uint32_t mlen, uint32_t lab, const uint8_t *str, uint32_t slen)
+{
+    NameWalk<P> w; w.init(m, mlen, lab);
     uint32_t k = 0; int c; bool first = true;
     while ((c = w.next_label()) > 0) {
         if (!first) { if (k >= slen || str[k] != '.') return false; k++; }
         first = false;
-        for (int i = 0; i < c; i++) { if (k >= slen || str[k] != lower(gb(m + w.p + i))) return false; k++; }
+        for (int i = 0; i < c; i++) { if (k >= slen || str[k] != lower(gb(m + (w.p + i)))) return false; k++; }
         w.p += c;
     }
     return c == 0 && k == slen;
@@ -73,12 +110,13 @@ __device__ __forceinline__ bool dns_name_equals(const uint8_t *m, uint32_t mlen,
 //
 // Exact, simple form (re-hashes every candidate suffix): only reached when a hash hit fails its byte
 // confirmation in the converged routine below, i.e. on a 64-bit hash collision.
-__device__ __noinline__ int dns_zone_select_exact(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t off, uint32_t *after, uint32_t *zone_hash)
+template <class P>
+__device__ __noinline__ int dns_zone_select_exact(const DevTables &T, P m, uint32_t mlen, uint32_t off, uint32_t *after, uint32_t *zone_hash)
 {
-    NameWalk w; w.init(m, mlen, off);
+    NameWalk<P> w; w.init(m, mlen, off);
     int labels = 0, last_bad = -1, c;
     while ((c = w.next_label()) > 0) {
-        for (int i = 0; i < c; i++) if (!zone_char(lower(gb(m + w.p + i)))) last_bad = labels;
+        for (int i = 0; i < c; i++) if (!zone_char(lower(gb(m + (w.p + i))))) last_bad = labels;
         labels++; w.p += c;
     }
     if (c < 0) return -1;
@@ -88,16 +126,16 @@ __device__ __noinline__ int dns_zone_select_exact(const DevTables &T, const uint
     for (int lab = 0; (c = w.next_label()) > 0; lab++) {
         const uint32_t lab_off = w.p - 1;
         if (lab > last_bad) {
-            NameWalk v; v.init(m, mlen, lab_off);                   // hash the suffix starting at this label
+            NameWalk<P> v; v.init(m, mlen, lab_off);                // hash the suffix starting at this label
             uint32_t h1 = 0, h2 = 0, p1 = 1, p2 = 1, len = 0; int cc; bool first = true;
             while ((cc = v.next_label()) > 0) {
                 if (!first) { h1 += '.' * p1; h2 += '.' * p2; p1 *= NAME_B1; p2 *= NAME_B2; len++; }
                 first = false;
-                for (int i = 0; i < cc; i++) { uint32_t ch = lower(gb(m + v.p + i)); h1 += ch * p1; h2 += ch * p2; p1 *= NAME_B1; p2 *= NAME_B2; len++; }
+                for (int i = 0; i < cc; i++) { uint32_t ch = lower(gb(m + (v.p + i))); h1 += ch * p1; h2 += ch * p2; p1 *= NAME_B1; p2 *= NAME_B2; len++; }
                 v.p += cc;
             }
             const uint64_t key = name_key(h1, h2, len);
-            uint32_t h = mix64(key) & T.zone_mask; NameSlot s;
+            uint32_t h = name_home(key, T.zone_mask); NameSlot s;
             while (name_table_find(T.zone_slots, T.zone_mask, key, h, s)) {
                 const uint8_t *str = T.names + s.str_off;
                 if (str[0] == len && dns_name_equals(m, mlen, lab_off, str + 1, len)) { *zone_hash = s.val; return 1; }
@@ -108,116 +146,107 @@ __device__ __noinline__ int dns_zone_select_exact(const DevTables &T, const uint
     return 0;
 }
 
-// Converged form: a warp whose 32 lanes each hold a different DNS name advances label by label in lock step
-// through two forward passes (F = whole-name sum, then prefix sums), every lane stops at its FIRST hash
-// hit (the longest matching suffix), and the byte-for-byte confirmation runs once after the loop.
-__device__ __noinline__ int dns_zone_select(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t off, uint32_t *after, uint32_t *zone_hash)
+// Lock-step form (one lane per name).  CONVERGENCE DISCIPLINE: `mask` names the lanes that entered together; every one
+// of them executes every __syncwarp(mask) below (no early return before the last one), the loops between two syncs are
+// flat (per-lane trip counts, no way out but the loop exit), and lanes that have nothing to do (`live` false, no
+// candidate, no hit) run them with zero trips.  Without the explicit syncs the compiler threads the exits of the hop
+// loop straight into the code that follows and the lanes of a warp run the scan one after another.
+//   1. hop over the length octets once (a 64-bit mask remembers where they are) — requires an uncompressed name
+//      shorter than 64 octets, i.e. every real question name; anything else takes the exact routine above;
+//   2. ONE right-to-left Horner pass gives the hash of every label suffix; only suffixes of at most
+//      T.zone_max_labels labels can be zones, so at most four candidate keys are kept (more labels in the
+//      table -> exact routine) and the pass stops as soon as no further candidate is possible;
+//   3. all candidates are looked up at once (one aligned 32-byte load each, independent, so a single L2 round trip);
+//   4. the longest hit is confirmed byte-for-byte in one flat loop.
+#define DNS_MAX_CAND 4
+template <class P>
+__device__ __noinline__ int dns_zone_select(const DevTables &T, P m, uint32_t mlen, uint32_t off, bool live, unsigned mask, uint32_t *after, uint32_t *zone_hash)
 {
-    // Common case first: an uncompressed name shorter than 64 octets (every real question name).  Hop over the
-    // length octets once (remembering where they are in a 64-bit mask), then ONE right-to-left Horner pass
-    // yields the hash of every label suffix; lanes move label by label in lock step; the longest hash hit is
-    // confirmed once at the end.  Anything else (pointers, long names, malformed) takes the general path below.
-    {
-        uint32_t pos = off; unsigned long long lm = 0ull; bool simple = true;
-        for (;;) {
-            if (pos >= mlen) { simple = false; break; }
+    uint32_t pos = off; unsigned long long lm = 0ull; bool walking = live, simple = false;
+    while (walking) {
+        if (pos >= mlen) walking = false;
+        else {
             const uint32_t l = gb(m + pos);
-            if (l == 0) break;
-            if ((l & 0xC0u) || pos + 1 + l > mlen || pos + 1 + l - off >= 64) { simple = false; break; }
-            lm |= 1ull << (pos - off);
-            pos += 1 + l;
-        }
-        if (simple) {
-            const uint32_t end = pos;                           // the root label's zero octet
-            *after = end + 1;
-            if (end == off || T.zone_slots == nullptr) return 0;
-            uint32_t S1 = 0, S2 = 0, i = end, hit_off = 0, hit_len = 0; bool bad = false, found = false; NameSlot hit, cand;
-            for (;;) {
-                bool isl;
-                do {
-                    i--;
-                    const uint32_t b = gb(m + i);
-                    isl = (lm >> (i - off)) & 1ull;
-                    if (!isl) { const uint32_t ch = lower(b); bad |= !zone_char(ch); S1 = ch + NAME_B1 * S1; S2 = ch + NAME_B2 * S2; }
-                } while (!isl);
-                if (bad) break;                                 // no zone can contain this label, nor any longer suffix
-                const uint64_t key = name_key(S1, S2, end - i - 1);
-                uint32_t h = mix64(key) & T.zone_mask;
-                if (name_table_find(T.zone_slots, T.zone_mask, key, h, cand)) { found = true; hit = cand; hit_off = i; hit_len = end - i - 1; }
-                if (i == off) break;
-                S1 = '.' + NAME_B1 * S1; S2 = '.' + NAME_B2 * S2;
-            }
-            if (!found) return 0;
-            // byte confirmation of the one hash hit: the dotted form of the suffix is the wire bytes with every
-            // length octet (known from lm) read as '.', so it is one flat loop, no label walk
-            const uint8_t *str = T.names + hit.str_off;
-            bool same = str[0] == hit_len;
-            for (uint32_t k = 0; same && k < hit_len; k++) {
-                const uint32_t pos = hit_off + 1 + k;
-                const uint32_t ch = ((lm >> (pos - off)) & 1ull) ? (uint32_t)'.' : lower(gb(m + pos));
-                same = str[1 + k] == ch;
-            }
-            if (same) { *zone_hash = hit.val; return 1; }
-            return dns_zone_select_exact(T, m, mlen, off, after, zone_hash);
+            if (l == 0) { simple = true; walking = false; }
+            else if ((l & 0xC0u) || pos + 1 + l > mlen || pos + 1 + l - off >= 64) walking = false;
+            else { lm |= 1ull << (pos - off); pos += 1 + l; }
         }
     }
-    NameWalk w; w.init(m, mlen, off);
-    uint32_t F1 = 0, F2 = 0, p1 = 1, p2 = 1, n = 0; int labels = 0, last_bad = -1, c;
-    while ((c = w.next_label()) > 0) {
-        if (labels) { F1 += '.' * p1; F2 += '.' * p2; p1 *= NAME_B1; p2 *= NAME_B2; n++; }
-        for (int i = 0; i < c; i++) {
-            const uint32_t b = lower(gb(m + w.p + i));
-            if (!zone_char(b)) last_bad = labels;
-            F1 += b * p1; F2 += b * p2; p1 *= NAME_B1; p2 *= NAME_B2; n++;
+    simple = simple && T.zone_max_labels <= DNS_MAX_CAND;
+    __syncwarp(mask);
+    const uint32_t end = pos;                               // the root label's zero octet (simple names)
+    int res = 0; uint32_t zh = 0, aft = end + 1;
+    uint64_t ck[DNS_MAX_CAND]; uint32_t cpos[DNS_MAX_CAND];
+    #pragma unroll
+    for (int c = 0; c < DNS_MAX_CAND; c++) { ck[c] = 0; cpos[c] = 0; }
+    uint32_t S1 = 0, S2 = 0, nlab = 0;
+    const uint32_t want = (simple && T.zone_slots != nullptr) ? T.zone_max_labels : 0u;
+    for (uint32_t i = end; i > off && nlab < want;) {        // flat: one octet per trip; stops at a bad label or after `want` labels
+        i--;
+        const uint32_t b = gb(m + i);
+        if ((lm >> (i - off)) & 1ull) {
+            const uint64_t key = name_key(S1, S2, end - i - 1);
+            #pragma unroll
+            for (int c = 0; c < DNS_MAX_CAND; c++) if ((uint32_t)c == nlab) { ck[c] = key; cpos[c] = i; }
+            nlab++;
+            S1 = '.' + NAME_B1 * S1; S2 = '.' + NAME_B2 * S2;
+        } else {
+            const uint32_t ch = lower(b);
+            if (!zone_char(ch)) break;                      // no zone contains this label, nor any longer suffix
+            S1 = ch + NAME_B1 * S1; S2 = ch + NAME_B2 * S2;
         }
-        labels++; w.p += c;
     }
-    if (c < 0) return -1;
-    *after = w.after;
-    if (T.zone_slots == nullptr) return 0;
-    w.init(m, mlen, off);
-    uint32_t P1 = 0, P2 = 0, i1 = 1, i2 = 1, k = 0, hit_off = 0, hit_len = 0; p1 = 1; p2 = 1;
-    int lab = 0; bool found = false; NameSlot hit;
-    for (;;) {
-        c = w.next_label();
-        if (c <= 0) break;
-        const uint32_t lab_off = w.p - 1;
-        if (lab) { P1 += '.' * p1; P2 += '.' * p2; p1 *= NAME_B1; p2 *= NAME_B2; i1 *= NAME_B1INV; i2 *= NAME_B2INV; k++; }
-        if (lab > last_bad) {
-            const uint64_t key = name_key((F1 - P1) * i1, (F2 - P2) * i2, n - k);
-            uint32_t h = mix64(key) & T.zone_mask;
-            if (name_table_find(T.zone_slots, T.zone_mask, key, h, hit)) { found = true; hit_off = lab_off; hit_len = n - k; break; }
+    __syncwarp(mask);
+    NamePair pr[DNS_MAX_CAND];
+    #pragma unroll
+    for (int c = 0; c < DNS_MAX_CAND; c++) if ((uint32_t)c < nlab) pr[c] = name_pair_load(T.zone_slots, T.zone_mask, ck[c]);
+    NameSlot hit; bool found = false; uint32_t hit_off = 0; hit.val = 0; hit.str_off = 0;
+    #pragma unroll
+    for (int c = DNS_MAX_CAND - 1; c >= 0; c--) {             // most labels first = longest suffix
+        if ((uint32_t)c < nlab && !found) {
+            NameSlot cand; int r = name_pair_decide(pr[c], ck[c], cand);
+            if (r == 2) r = name_table_find_from(T.zone_slots, T.zone_mask, ck[c], 2, cand) ? 1 : 0;
+            if (r == 1) { found = true; hit = cand; hit_off = cpos[c]; }
         }
-        for (int i = 0; i < c; i++) {
-            const uint32_t b = lower(gb(m + w.p + i));
-            P1 += b * p1; P2 += b * p2; p1 *= NAME_B1; p2 *= NAME_B2; i1 *= NAME_B1INV; i2 *= NAME_B2INV; k++;
-        }
-        lab++; w.p += c;
     }
-    if (!found) return 0;
+    __syncwarp(mask);
+    // byte confirmation of the one hash hit: the dotted form of the suffix is the wire bytes with every length octet
+    // (known from lm) read as '.', so it is one flat loop, no label walk
+    const uint32_t hit_len = found ? end - hit_off - 1 : 0u;
     const uint8_t *str = T.names + hit.str_off;
-    if (str[0] == hit_len && dns_name_equals(m, mlen, hit_off, str + 1, hit_len)) { *zone_hash = hit.val; return 1; }
-    return dns_zone_select_exact(T, m, mlen, off, after, zone_hash);
+    bool same = found && str[0] == hit_len;
+    for (uint32_t k = 0; k < (same ? hit_len : 0u); k++) {
+        const uint32_t q = hit_off + 1 + k;
+        const uint32_t ch = ((lm >> (q - off)) & 1ull) ? (uint32_t)'.' : lower(gb(m + q));
+        same &= str[1 + k] == ch;
+    }
+    if (same) { res = 1; zh = hit.val; }
+    __syncwarp(mask);
+    if (live && (!simple || (found && !same)))               // compressed / long / malformed names, >4-label tables, a 64-bit key collision
+        res = dns_zone_select_exact(T, m, mlen, off, &aft, &zh);
+    __syncwarp(mask);
+    *after = aft; *zone_hash = zh;
+    return res;
 }
 
-// DNS query arriving at CoreDNS (miekg/dns defaultMsgAcceptFunc, then ServeDNS zone routing).
-__device__ __forceinline__ uint32_t dns_query_verdict(const DevTables &T, const uint8_t *m, uint32_t mlen)
+// DNS query arriving at CoreDNS (miekg/dns defaultMsgAcceptFunc, then ServeDNS zone routing).  Every lane of `mask` calls.
+template <class P>
+__device__ __forceinline__ uint32_t dns_query_verdict(const DevTables &T, P m, uint32_t mlen, unsigned mask)
 {
-    if (mlen < 12) return CLK_N_DENY;
-    uint32_t fl = gbe16(m + 2);
-    if (fl & 0x8000u) return CLK_N_DENY;
-    uint32_t opcode = (fl >> 11) & 15u;
-    if (opcode != 0 && opcode != 4) return CLK_N_DENY;
-    if (gbe16(m + 4) != 1) return CLK_N_DENY;
-    if (gbe16(m + 6) > 1 || gbe16(m + 8) > 1 || gbe16(m + 10) > 2) return CLK_N_DENY;
+    bool live = mlen >= 12;
+    if (live) {
+        const uint32_t fl = gbe16(m + 2u), opcode = (fl >> 11) & 15u;
+        live = !(fl & 0x8000u) && (opcode == 0 || opcode == 4) && gbe16(m + 4u) == 1 && gbe16(m + 6u) <= 1 && gbe16(m + 8u) <= 1 && gbe16(m + 10u) <= 2;
+    }
     uint32_t after, zh;
-    int z = dns_zone_select(T, m, mlen, 12, &after, &zh);
-    if (z < 0 || after + 4 > mlen) return CLK_N_DENY;
-    if (gbe16(m + after + 2) != 1) return CLK_N_DENY;
+    const int z = dns_zone_select(T, m, mlen, 12, live, mask, &after, &zh);
+    if (!live || z < 0 || after + 4 > mlen) return CLK_N_DENY;
+    if (gbe16(m + (after + 2)) != 1) return CLK_N_DENY;
     return z == 1 ? CLK_N_ALLOW : CLK_N_DENY;
 }
 
-__device__ __forceinline__ int dns_skip_name(const uint8_t *m, uint32_t mlen, uint32_t &p)
+template <class P>
+__device__ __forceinline__ int dns_skip_name(P m, uint32_t mlen, uint32_t &p)
 {
     uint32_t wire = 0;
     for (;;) {
@@ -231,40 +260,45 @@ __device__ __forceinline__ int dns_skip_name(const uint8_t *m, uint32_t mlen, ui
     }
 }
 
-// dnsbpf.Handler.writeARecords over the wire form.  out == nullptr: count only.
-__device__ __noinline__ uint32_t dns_answer_updates(const DevTables &T, const uint8_t *m, uint32_t mlen, uint32_t pkt_index,
-                                                       clk_dns_update_rec *out, unsigned long long pos, unsigned long long cap, uint32_t *name_v)
+// dnsbpf.Handler.writeARecords over the wire form.  out == nullptr: count only.  Every lane of `mask` calls.
+template <class P>
+__device__ __noinline__ uint32_t dns_answer_updates(const DevTables &T, P m, uint32_t mlen, uint32_t pkt_index,
+                                                       clk_dns_update_rec *out, unsigned long long pos, unsigned long long cap, uint32_t *name_v, unsigned mask)
 {
-    *name_v = CLK_N_DENY;
-    if (mlen < 12) return 0;
-    uint32_t fl = gbe16(m + 2);
-    if (!(fl & 0x8000u)) return 0;
-    if (gbe16(m + 4) != 1) return 0;
-    uint32_t an = gbe16(m + 6), rest = gbe16(m + 8) + gbe16(m + 10);
-    uint32_t off, zone_hash;
-    int z = dns_zone_select(T, m, mlen, 12, &off, &zone_hash);
-    if (z < 0 || off + 4 > mlen) return 0;
-    off += 4;
-    if (z != 1) return 0;
-    *name_v = CLK_N_ALLOW;
-    uint32_t p = off;
-    for (uint32_t i = 0; i < an + rest; i++) {                      // framing pass: any malformed RR voids the message
-        if (dns_skip_name(m, mlen, p)) return 0;
-        if (p + 10 > mlen) return 0;
-        uint32_t type = gbe16(m + p), rdlen = gbe16(m + p + 8);
-        if (p + 10 + rdlen > mlen) return 0;
-        if (i < an && type == 1 && rdlen != 4) return 0;
-        p += 10 + rdlen;
+    bool live = mlen >= 12;
+    uint32_t an = 0, rest = 0;
+    if (live) {
+        live = (gbe16(m + 2u) & 0x8000u) && gbe16(m + 4u) == 1;
+        an = gbe16(m + 6u); rest = gbe16(m + 8u) + gbe16(m + 10u);
     }
+    uint32_t off, zone_hash;
+    const int z = dns_zone_select(T, m, mlen, 12, live, mask, &off, &zone_hash);
+    live = live && z >= 0 && off + 4 <= mlen;
+    off += 4;
+    live = live && z == 1;
+    *name_v = live ? CLK_N_ALLOW : CLK_N_DENY;
+    uint32_t p = off;
+    const uint32_t total = live ? an + rest : 0u;
+    for (uint32_t i = 0; i < total; i++) {                          // framing pass: any malformed RR voids the message
+        bool ok = dns_skip_name(m, mlen, p) == 0 && p + 10 <= mlen;
+        if (ok) {
+            const uint32_t type = gbe16(m + p), rdlen = gbe16(m + (p + 8));
+            ok = p + 10 + rdlen <= mlen && !(i < an && type == 1 && rdlen != 4);
+            p += 10 + rdlen;
+        }
+        if (!ok) { live = false; break; }
+    }
+    __syncwarp(mask);
     uint32_t nupd = 0; p = off;
-    for (uint32_t i = 0; i < an; i++) {
+    const uint32_t n_an = live ? an : 0u;
+    for (uint32_t i = 0; i < n_an; i++) {
         dns_skip_name(m, mlen, p);
-        uint32_t type = gbe16(m + p), rdlen = gbe16(m + p + 8);
+        uint32_t type = gbe16(m + p), rdlen = gbe16(m + (p + 8));
         if (type == 1) {
-            uint32_t ip = gb(m + p + 10) | (gb(m + p + 11) << 8) | (gb(m + p + 12) << 16) | (gb(m + p + 13) << 24);
+            uint32_t ip = gb(m + (p + 10)) | (gb(m + (p + 11)) << 8) | (gb(m + (p + 12)) << 16) | (gb(m + (p + 13)) << 24);
             if (ip != 0 && nupd < CLK_MAX_A_PER_PACKET) {
                 if (out && pos + nupd < cap) {
-                    uint32_t ttl = (gbe16(m + p + 4) << 16) | gbe16(m + p + 6);
+                    uint32_t ttl = (gbe16(m + (p + 4)) << 16) | gbe16(m + (p + 6));
                     clk_dns_update_rec r; r.ip = ip; r.domain_hash = zone_hash; r.ttl = ttl ? ttl : 60u; r.packet = pkt_index;
                     out[pos + nupd] = r;
                 }
@@ -273,6 +307,7 @@ __device__ __noinline__ uint32_t dns_answer_updates(const DevTables &T, const ui
         }
         p += 10 + rdlen;
     }
+    __syncwarp(mask);
     return nupd;
 }
 
@@ -280,7 +315,7 @@ __device__ __forceinline__ uint32_t dns_answer_word(const DevTables &T, const ui
 {
     uint32_t po = p.l4off + 8;
     if (po > p.end) return 0;
-    uint32_t nv, n = dns_answer_updates(T, pk + po, p.end - po, 0, nullptr, 0, 0, &nv);
+    uint32_t nv, n = dns_answer_updates(T, pk + po, p.end - po, 0, nullptr, 0, 0, &nv, __activemask());
     return (nv << 4) | (n << 27);
 }
 
@@ -292,18 +327,20 @@ __device__ __forceinline__ void dns_answer_extract(const DevTables &T, const uin
     uint32_t end = 14 + gbe16(pk + 16); if (end > avail) end = avail;
     uint32_t po = l4off + 8, nv;
     if (po > end) return;
-    dns_answer_updates(T, pk + po, end - po, pkt_index, out, pos, cap, &nv);
+    dns_answer_updates(T, pk + po, end - po, pkt_index, out, pos, cap, &nv, __activemask());
 }
 
 // ---- TLS ClientHello -> SNI -> Envoy server_names ----------------------------------------------------------
-__device__ __forceinline__ bool sni_equals(const uint8_t *host, uint32_t from, uint32_t n, const uint8_t *str)
+template <class P>
+__device__ __forceinline__ bool sni_equals(P host, uint32_t from, uint32_t n, const uint8_t *str)
 {
     if (str[0] != n - from) return false;
     for (uint32_t i = from; i < n; i++) if (str[1 + i - from] != lower(gb(host + i))) return false;
     return true;
 }
 
-__device__ __noinline__ bool sni_match_exact(const DevTables &T, const uint8_t *host, uint32_t n)
+template <class P>
+__device__ __noinline__ bool sni_match_exact(const DevTables &T, P host, uint32_t n)
 {
     // simple form: re-hash every candidate suffix (whole name, then each '.' at 1 <= pos < n - 1)
     if (T.sni_slots == nullptr) return false;
@@ -312,69 +349,124 @@ __device__ __noinline__ bool sni_match_exact(const DevTables &T, const uint8_t *
         uint32_t h1 = 0, h2 = 0, p1 = 1, p2 = 1;
         for (uint32_t i = pos; i < n; i++) { uint32_t ch = lower(gb(host + i)); h1 += ch * p1; h2 += ch * p2; p1 *= NAME_B1; p2 *= NAME_B2; }
         const uint64_t key = name_key(h1, h2, n - pos);
-        uint32_t h = mix64(key) & T.sni_mask; NameSlot s;
+        uint32_t h = name_home(key, T.sni_mask); NameSlot s;
         while (name_table_find(T.sni_slots, T.sni_mask, key, h, s))
             if (sni_equals(host, pos, n, T.names + s.str_off)) return true;
     }
     return false;
 }
 
-// Converged form: one right-to-left Horner pass gives the hash of every suffix; lanes move from candidate
-// to candidate in lock step (any match allows, so the order is irrelevant), stop at their first hash hit and
-// confirm once after the loop.
-__device__ __forceinline__ bool sni_match(const DevTables &T, const uint8_t *host, uint32_t n)
+// Lock-step form (same convergence discipline as dns_zone_select: every lane of `mask` calls and passes every
+// __syncwarp; a lane without a name comes with n == 0): one flat right-to-left Horner pass gives the hash of every
+// dot-suffix; a wildcard server_name ".d" can only equal a suffix with at most T.sni_max_dots dots, so at most
+// SNI_MAX_CAND suffix candidates are kept (more dots in the table -> exact routine) next to the whole name; all
+// candidates are looked up at once (one aligned 32-byte load each), any hit allows, and the hit is confirmed
+// byte-for-byte in one flat loop.  *has_nul: the name contains a NUL octet (the caller denies it).
+#define SNI_MAX_CAND 4
+template <class P>
+__device__ __forceinline__ bool sni_match(const DevTables &T, P host, uint32_t n, unsigned mask, bool *has_nul)
 {
-    if (T.sni_slots == nullptr) return false;
-    uint32_t S1 = 0, S2 = 0, i = n; bool found = false; NameSlot hit;
-    for (;;) {
-        uint32_t c;
-        do { i--; c = lower(gb(host + i)); S1 = c + NAME_B1 * S1; S2 = c + NAME_B2 * S2; } while (i > 0 && !(c == '.' && i + 1 < n));
-        // here: i == 0 (the whole name) or host[i] is a '.' with 1 <= i < n - 1 (Envoy's wildcard candidates)
-        const uint64_t key = name_key(S1, S2, n - i);
-        uint32_t h = mix64(key) & T.sni_mask;
-        if (name_table_find(T.sni_slots, T.sni_mask, key, h, hit)) { found = true; break; }
-        if (i == 0) break;
+    const bool fast = T.sni_slots != nullptr && T.sni_max_dots <= SNI_MAX_CAND;
+    uint64_t ck[SNI_MAX_CAND + 1]; uint32_t cpos[SNI_MAX_CAND + 1];
+    #pragma unroll
+    for (int c = 0; c <= SNI_MAX_CAND; c++) { ck[c] = 0; cpos[c] = 0; }
+    uint32_t S1 = 0, S2 = 0, ndot = 0; bool nul = false;
+    const uint32_t want = T.sni_max_dots;
+    for (uint32_t i = n; i > 0;) {                           // flat: one byte per trip
+        i--;
+        const uint32_t b = gb(host + i), c = lower(b);
+        nul |= b == 0;
+        S1 = c + NAME_B1 * S1; S2 = c + NAME_B2 * S2;
+        if (c == '.' && i >= 1 && i + 1 < n && ndot < want) {   // Envoy's wildcard candidates: ".suffix" starting at a dot inside the name
+            const uint64_t key = name_key(S1, S2, n - i);
+            #pragma unroll
+            for (int k = 0; k < SNI_MAX_CAND; k++) if ((uint32_t)k == ndot) { ck[k + 1] = key; cpos[k + 1] = i; }
+            ndot++;
+        }
     }
-    if (!found) return false;
-    if (sni_equals(host, i, n, T.names + hit.str_off)) return true;
-    return sni_match_exact(T, host, n);
+    *has_nul = nul;
+    ck[0] = name_key(S1, S2, n);                             // the whole name
+    const bool look = fast && n > 0 && !nul;
+    __syncwarp(mask);
+    NamePair pr[SNI_MAX_CAND + 1];
+    #pragma unroll
+    for (int c = 0; c <= SNI_MAX_CAND; c++) if (look && (uint32_t)c <= ndot) pr[c] = name_pair_load(T.sni_slots, T.sni_mask, ck[c]);
+    NameSlot hit; bool found = false; uint32_t from = 0; hit.val = 0; hit.str_off = 0;
+    #pragma unroll
+    for (int c = 0; c <= SNI_MAX_CAND; c++) {
+        if (look && (uint32_t)c <= ndot && !found) {
+            NameSlot cand; int r = name_pair_decide(pr[c], ck[c], cand);
+            if (r == 2) r = name_table_find_from(T.sni_slots, T.sni_mask, ck[c], 2, cand) ? 1 : 0;
+            if (r == 1) { found = true; hit = cand; from = cpos[c]; }
+        }
+    }
+    __syncwarp(mask);
+    const uint8_t *str = T.names + hit.str_off;
+    bool same = found && str[0] == n - from;
+    for (uint32_t i = from; i < (same ? n : from); i++) same &= str[1 + i - from] == lower(gb(host + i));
+    bool res = same;
+    __syncwarp(mask);
+    if (n > 0 && !nul && T.sni_slots != nullptr && (!fast || (found && !same)))      // >4-dot wildcards in the table, or a 64-bit key collision
+        res = sni_match_exact(T, host, n);
+    __syncwarp(mask);
+    return res;
 }
 
-__device__ __noinline__ uint32_t tls_sni_verdict(const DevTables &T, const uint8_t *p, uint32_t n)
+// Walks the ClientHello of one segment up to the server_name extension.  Returns 0 with the host name at p + *sni_off
+// (*snl octets), or the verdict that is already decided: a ClientHello that does not fit the segment (record or
+// handshake longer than the captured payload: large key shares, post-quantum hybrids) cannot be judged from this
+// packet — Envoy's tls_inspector keeps buffering — N/A ("needs reassembly"), like an incomplete HTTP request;
+// complete-but-malformed records, or none / several server_name extensions, are DENY.
+template <class P>
+__device__ __noinline__ uint32_t tls_locate_sni(P p, uint32_t n, uint32_t *sni_off, uint32_t *snl_out)
 {
-    if (n < 9 || gb(p) != 0x16u || gb(p + 1) != 0x03u) return CLK_N_DENY;
-    uint32_t rlen = gbe16(p + 3);
-    if (5 + rlen > n) return CLK_N_DENY;
-    const uint8_t *h = p + 5;
+    *sni_off = 0; *snl_out = 0;
+    if (n < 9 || gb(p) != 0x16u || gb(p + 1u) != 0x03u) return CLK_N_DENY;
+    uint32_t rlen = gbe16(p + 3u);
+    if (5 + rlen > n) return CLK_N_NA + 4;                                  // (+4: "decided N/A", see the caller)
+    const P h = p + 5u;
     if (gb(h) != 1) return CLK_N_DENY;
-    uint32_t hl = (gb(h + 1) << 16) | (gb(h + 2) << 8) | gb(h + 3);
-    if (4 + hl > rlen) return CLK_N_DENY;
-    const uint8_t *b = h + 4;
+    uint32_t hl = (gb(h + 1u) << 16) | (gb(h + 2u) << 8) | gb(h + 3u);
+    if (4 + hl > rlen) return CLK_N_NA + 4;                                 // the handshake message continues in the next record
+    const P b = h + 4u;
     if (hl < 35) return CLK_N_DENY;
     uint32_t o = 34;
     uint32_t sl = gb(b + o); o += 1 + sl; if (o + 2 > hl) return CLK_N_DENY;
     uint32_t cl = gbe16(b + o); o += 2 + cl; if (o + 1 > hl) return CLK_N_DENY;
     uint32_t ml = gb(b + o); o += 1 + ml; if (o + 2 > hl) return CLK_N_DENY;
     uint32_t el = gbe16(b + o); o += 2; if (o + el != hl) return CLK_N_DENY;
-    const uint8_t *sni = nullptr; uint32_t snl = 0; bool seen = false;
+    uint32_t so = 0, snl = 0; bool seen = false;
     while (o + 4 <= hl) {
-        uint32_t et = gbe16(b + o), xl = gbe16(b + o + 2); o += 4;
+        uint32_t et = gbe16(b + o), xl = gbe16(b + (o + 2)); o += 4;
         if (o + xl > hl) return CLK_N_DENY;
         if (et == 0) {
             if (seen) return CLK_N_DENY;
             seen = true;
             if (xl < 5) return CLK_N_DENY;
             uint32_t ll = gbe16(b + o);
-            if (ll + 2 != xl || gb(b + o + 2) != 0) return CLK_N_DENY;
-            snl = gbe16(b + o + 3);
+            if (ll + 2 != xl || gb(b + (o + 2)) != 0) return CLK_N_DENY;
+            snl = gbe16(b + (o + 3));
             if (snl == 0 || snl > 255 || snl + 3 != ll) return CLK_N_DENY;
-            sni = b + o + 5;
+            so = 9 + o + 5;                                                  // relative to p: record header 5 + handshake header 4
         }
         o += xl;
     }
-    if (o != hl || !sni) return CLK_N_DENY;
-    for (uint32_t i = 0; i < snl; i++) if (gb(sni + i) == 0) return CLK_N_DENY;
-    return sni_match(T, sni, snl) ? CLK_N_ALLOW : CLK_N_DENY;
+    if (o != hl || !seen) return CLK_N_DENY;
+    *sni_off = so; *snl_out = snl;
+    return 0;
+}
+
+// Every lane of `mask` calls.
+template <class P>
+__device__ __noinline__ uint32_t tls_sni_verdict(const DevTables &T, P p, uint32_t n, unsigned mask)
+{
+    uint32_t so, snl;
+    const uint32_t early = tls_locate_sni(p, n, &so, &snl);
+    __syncwarp(mask);                                        // the walk leaves through many exits: gather the lanes again
+    bool nul;
+    const bool allow = sni_match(T, p + so, early ? 0u : snl, mask, &nul);
+    if (early) return early & 3u;
+    return (!nul && allow) ? CLK_N_ALLOW : CLK_N_DENY;
 }
 
 // ---- plaintext HTTP on the egress listener: Host -> virtual host -> first matching path prefix -----
@@ -385,16 +477,18 @@ __device__ __noinline__ uint32_t tls_sni_verdict(const DevTables &T, const uint8
 // no CRLF yet, or the segment ends inside the header block before a Host line -> N/A (needs reassembly); not an
 // HTTP/1.x request line, CONNECT, no Host, no virtual host or no route -> DENY; an absolute-form target
 // "http://authority/path" replaces Host by its authority.
-__device__ __forceinline__ int http_table_lookup(const DevTables &T, uint32_t h1, uint32_t h2, uint32_t kind, const uint8_t *host, uint32_t from, uint32_t to)
+template <class P>
+__device__ __forceinline__ int http_table_lookup(const DevTables &T, uint32_t h1, uint32_t h2, uint32_t kind, P host, uint32_t from, uint32_t to)
 {
     const uint64_t key = name_key(h1, h2, to - from);
-    uint32_t h = mix64(key) & T.http_mask; NameSlot s;
+    uint32_t h = name_home(key, T.http_mask); NameSlot s;
     while (name_table_find(T.http_slots, T.http_mask, key, h, s))
         if ((s.val >> 28) == kind && sni_equals(host, from, to, T.names + s.str_off)) return (int)(s.val & 0x0fffffffu);
     return -1;
 }
 
-__device__ __forceinline__ int http_vhost_find(const DevTables &T, const uint8_t *host, uint32_t hn)
+template <class P>
+__device__ __forceinline__ int http_vhost_find(const DevTables &T, P host, uint32_t hn)
 {
     uint32_t F1 = 0, F2 = 0, p1 = 1, p2 = 1, colons = 0;
     for (uint32_t i = 0; i < hn; i++) { const uint32_t c = lower(gb(host + i)); F1 += c * p1; F2 += c * p2; p1 *= NAME_B1; p2 *= NAME_B2; colons += c == ':'; }
@@ -432,10 +526,11 @@ __device__ __forceinline__ bool http_token_char(uint32_t c)
     return true;
 }
 
-__device__ __noinline__ uint32_t http_host_verdict(const DevTables &T, const uint8_t *p, uint32_t n)
+template <class P>
+__device__ __noinline__ uint32_t http_host_verdict(const DevTables &T, P p, uint32_t n)
 {
     uint32_t eol = 0;
-    while (eol + 1 < n && !(gb(p + eol) == '\r' && gb(p + eol + 1) == '\n')) eol++;
+    while (eol + 1 < n && !(gb(p + eol) == '\r' && gb(p + (eol + 1)) == '\n')) eol++;
     if (eol + 1 >= n) return CLK_N_NA;                                  // request line not complete in this segment
     uint32_t m = 0;
     while (m < eol && http_token_char(gb(p + m))) m++;
@@ -446,35 +541,35 @@ __device__ __noinline__ uint32_t http_host_verdict(const DevTables &T, const uin
     if (eol - te != 9) return CLK_N_DENY;
     {   // " HTTP/1.0" | " HTTP/1.1"
         const char *lit = "HTTP/1.";
-        for (int i = 0; i < 7; i++) if (gb(p + te + 1 + i) != (uint32_t)lit[i]) return CLK_N_DENY;
-        const uint32_t d = gb(p + te + 8);
+        for (int i = 0; i < 7; i++) if (gb(p + (te + 1 + i)) != (uint32_t)lit[i]) return CLK_N_DENY;
+        const uint32_t d = gb(p + (te + 8));
         if (d != '0' && d != '1') return CLK_N_DENY;
     }
-    if (m == 7) { const char *lit = "CONNECT"; bool is = true; for (int i = 0; i < 7; i++) is &= gb(p + i) == (uint32_t)lit[i]; if (is) return CLK_N_DENY; }
-    const uint8_t *host = nullptr; uint32_t hn = 0; const uint8_t *path = p + ts; uint32_t pn = te - ts; bool root_path = false;
-    if (pn >= 7 && (gb(p + ts) | 32u) == 'h' && (gb(p + ts + 1) | 32u) == 't' && (gb(p + ts + 2) | 32u) == 't' && (gb(p + ts + 3) | 32u) == 'p' &&
-        gb(p + ts + 4) == ':' && gb(p + ts + 5) == '/' && gb(p + ts + 6) == '/') {                    // absolute-form: the authority replaces Host
+    if (m == 7) { const char *lit = "CONNECT"; bool is = true; for (int i = 0; i < 7; i++) is &= gb(p + (uint32_t)i) == (uint32_t)lit[i]; if (is) return CLK_N_DENY; }
+    P host = p; bool have_host = false; uint32_t hn = 0; P path = p + ts; uint32_t pn = te - ts; bool root_path = false;
+    if (pn >= 7 && (gb(p + ts) | 32u) == 'h' && (gb(p + (ts + 1)) | 32u) == 't' && (gb(p + (ts + 2)) | 32u) == 't' && (gb(p + (ts + 3)) | 32u) == 'p' &&
+        gb(p + (ts + 4)) == ':' && gb(p + (ts + 5)) == '/' && gb(p + (ts + 6)) == '/') {                    // absolute-form: the authority replaces Host
         uint32_t a = ts + 7, b = a;
         while (b < te && gb(p + b) != '/') b++;
-        host = p + a; hn = b - a;
+        host = p + a; hn = b - a; have_host = true;
         if (b < te) { path = p + b; pn = te - b; } else { root_path = true; pn = 1; }
     }
     bool complete = false;
-    for (uint32_t ls = eol + 2; host == nullptr;) {                      // header lines
+    for (uint32_t ls = eol + 2; !have_host;) {                           // header lines
         uint32_t le = ls;
-        while (le + 1 < n && !(gb(p + le) == '\r' && gb(p + le + 1) == '\n')) le++;
+        while (le + 1 < n && !(gb(p + le) == '\r' && gb(p + (le + 1)) == '\n')) le++;
         if (le + 1 >= n) break;
         if (le == ls) { complete = true; break; }
-        if (le - ls >= 5 && (gb(p + ls) | 32u) == 'h' && (gb(p + ls + 1) | 32u) == 'o' && (gb(p + ls + 2) | 32u) == 's' && (gb(p + ls + 3) | 32u) == 't' && gb(p + ls + 4) == ':') {
+        if (le - ls >= 5 && (gb(p + ls) | 32u) == 'h' && (gb(p + (ls + 1)) | 32u) == 'o' && (gb(p + (ls + 2)) | 32u) == 's' && (gb(p + (ls + 3)) | 32u) == 't' && gb(p + (ls + 4)) == ':') {
             uint32_t a = ls + 5, b = le;
             while (a < b && (gb(p + a) == ' ' || gb(p + a) == '\t')) a++;
-            while (b > a && (gb(p + b - 1) == ' ' || gb(p + b - 1) == '\t')) b--;
-            host = p + a; hn = b - a;
+            while (b > a && (gb(p + (b - 1)) == ' ' || gb(p + (b - 1)) == '\t')) b--;
+            host = p + a; hn = b - a; have_host = true;
             break;
         }
         ls = le + 2;
     }
-    if (host == nullptr) { if (!complete) return CLK_N_NA; hn = 0; }    // no Host at all: only "*" could match
+    if (!have_host) { if (!complete) return CLK_N_NA; hn = 0; }        // no Host at all: only "*" could match
     if (hn == 0 || hn > 255) return CLK_N_DENY;
     const int v = http_vhost_find(T, host, hn);
     if (v < 0) return CLK_N_DENY;                                       // deny_all: 403
@@ -495,10 +590,11 @@ __device__ __noinline__ uint32_t http_host_verdict(const DevTables &T, const uin
 
 // tls_inspector: a first segment that is not a TLS handshake record is "raw_buffer" and takes the HTTP chain when
 // one is configured (envoy.go:358-372); without HTTP rules no filter chain matches (tls_sni_verdict denies it).
-__device__ __forceinline__ uint32_t egress_payload_verdict(const DevTables &T, const uint8_t *p, uint32_t n)
+template <class P>
+__device__ __forceinline__ uint32_t egress_payload_verdict(const DevTables &T, P p, uint32_t n)
 {
     if (T.n_http && n >= 1 && gb(p) != 0x16u) return http_host_verdict(T, p, n);
-    return tls_sni_verdict(T, p, n);
+    return tls_sni_verdict(T, p, n, __activemask());
 }
 
 // ---- gating: which payload stage applies to an egress packet ------------------------------
@@ -514,10 +610,10 @@ __device__ __forceinline__ uint32_t name_stage(const DevTables &T, const uint8_t
     uint32_t fport = d.verdict == CLK_V_REWRITE ? d.new_port : p.port;
     uint32_t po = 0, pl = 0;
     if (p.proto == 17) { po = p.l4off + 8; if (po <= p.end) pl = p.end - po; }
-    else if (p.l4off + 13 <= avail) { uint32_t doff = (gb(pk + p.l4off + 12) >> 4) * 4; po = p.l4off + doff; if (doff >= 20 && po <= p.end) pl = p.end - po; }
+    else if (p.l4off + 13 <= avail) { uint32_t doff = (gb(pk + (p.l4off + 12)) >> 4) * 4; po = p.l4off + doff; if (doff >= 20 && po <= p.end) pl = p.end - po; }
     if (fip == cfg->coredns_ip && fport == 53) {
-        if (p.proto == 17) return dns_query_verdict(T, pk + po, pl);
-        if (pl > 0) return (pl >= 2 && gbe16(pk + po) + 2 <= pl) ? dns_query_verdict(T, pk + po + 2, gbe16(pk + po)) : CLK_N_DENY;
+        if (p.proto == 17) return dns_query_verdict(T, pk + po, pl, __activemask());
+        if (pl > 0) return (pl >= 2 && gbe16(pk + po) + 2 <= pl) ? dns_query_verdict(T, pk + (po + 2), gbe16(pk + po), __activemask()) : CLK_N_DENY;
         return CLK_N_NA;
     }
     if (p.proto == 6 && fip == cfg->envoy_ip && fport == cfg->egress_port && pl > 0) return egress_payload_verdict(T, pk + po, pl);
