@@ -361,18 +361,17 @@ def measure(args, workload: str, full: bool) -> dict:
     # metrics_map max_entries: 8x the reference default (common.h:173) so every key of the synthetic capture is counted;
     # keys beyond max_entries are dropped like the reference BPF_NOEXIST insert into a full map (--metrics-capacity)
     # multi-GPU: the classify kernels leave a few SMs to the side stream so the per-batch collective never delays them
-    reserved = args.reserved_sms if args.reserved_sms >= 0 else (4 if world > 1 else 0)
+    reserved = args.reserved_sms if args.reserved_sms >= 0 else (4 if world > 1 and not varlen else 0)   # ms-long varlen steps do not need them
     e = engine.Engine(device=local, max_metrics=args.metrics_capacity, max_dns_cache=1 << 21, max_routes=1 << 16, max_containers=max(256, len(w.tables["containers"])),
                       reserved_sms=reserved)
     e.load_tables(w.tables)
     e.compile_rules(w.rules)
     e.publish()
-    rows = e.counters_block_rows()
-    d_block = torch.empty(rows * 24, dtype=torch.uint8, device=dev)
-    d_gather = torch.empty(world * rows * 24, dtype=torch.uint8, device=dev) if world > 1 else None
+    if world > 1:                                                  # the communicator lives behind the C ABI (clk_comm_*): NCCL over NVLink
+        ids = [engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        e.comm_init(ids[0], rank, world)
     trow = e.totals_rows()
-    d_tot = torch.zeros(trow * 32, dtype=torch.uint8, device=dev)
-    d_tot_all = torch.zeros(world * trow * 32, dtype=torch.uint8, device=dev) if world > 1 else None
 
     ts = torch.cuda.Stream(device=dev)
     side = torch.cuda.Stream(device=dev)                           # the collective overlaps the next batch's kernel
@@ -390,15 +389,10 @@ def measure(args, workload: str, full: bool) -> dict:
             ev_pair[1].record(ts)
         if world > 1:                                              # per batch: per-container totals of every GPU over NVLink
             side.wait_stream(ts)
-            with torch.cuda.stream(side):
-                e.totals_export(d_tot.data_ptr(), side.cuda_stream)
-                dist.all_gather_into_tensor(d_tot_all, d_tot)
+            e.allgather_counters(side.cuda_stream)                 # clk_allgather_counters: totals export + ncclAllGather, enqueue only
 
     def merge_on_read():                                           # per-key merge of the metrics_map tables: once per read
-        with torch.cuda.stream(side):
-            e.counters_export(d_block.data_ptr(), side.cuda_stream)
-            dist.all_gather_into_tensor(d_gather, d_block)
-            e.counters_import(d_gather.data_ptr(), world, side.cuda_stream)
+        e.allgather_metrics(side.cuda_stream)                      # clk_allgather_metrics: export + ncclAllGather + import
 
     sampler = ClockSampler(local) if rank == 0 else None          # attached and parked before the barrier: rank 0 must not start late
     if sampler:
@@ -473,7 +467,7 @@ def measure(args, workload: str, full: bool) -> dict:
         m1.record(side)
         torch.cuda.synchronize()
         merge_ms = m0.elapsed_time(m1)
-        tot = e.totals_merge(d_tot_all.data_ptr(), world)
+        tot = e.totals_global()
         mg = e.counters(merged=True)
         for a in range(3):                                         # the two forms of the sum must agree
             assert int(tot["count"][:, a].sum()) == int(mg["count"][mg["action"] == a].sum()), "per-container totals != merged metrics_map"
@@ -485,7 +479,7 @@ def measure(args, workload: str, full: bool) -> dict:
         if world > 1:
             side.wait_stream(ts)
             torch.cuda.synchronize()
-            tot1 = e.totals_merge(d_tot_all.data_ptr(), world)     # totals gathered by the parity pass: one batch per rank since the reset
+            tot1 = e.totals_global()                               # totals gathered by the parity pass: one batch per rank since the reset
             mine = torch.tensor([parity["checked"], parity["mismatches"], parity.get("counters", {}).get("mismatches", 0) or 0]
                                 + parity.get("totals_oracle", [0, 0, 0]), dtype=torch.int64, device=dev)
             dist.all_reduce(mine, op=dist.ReduceOp.SUM)
@@ -555,8 +549,8 @@ def measure(args, workload: str, full: bool) -> dict:
                 break
         cfg = config_of(spec, w, n, gen, world)
         if world > 1:
-            cfg["collective"] = (f"{trow * 32} B per GPU per step on a side stream, {reserved} SMs reserved; per-key metrics_map merge on read, "
-                                 f"outside the timed region ({merge_ms:.3f} ms per read)")
+            cfg["collective"] = (f"clk_allgather_counters (NCCL behind the C ABI): {trow * 32} B per GPU per step on a side stream, {reserved} SMs reserved; "
+                                 f"per-key metrics_map merge on read (clk_allgather_metrics), outside the timed region ({merge_ms:.3f} ms per read)")
         out = {
             "value": round(value, 1), "unit": "Mpackets/s", "ms_per_step": round(ms_per_step, 4), "config": cfg,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
@@ -575,7 +569,9 @@ def measure(args, workload: str, full: bool) -> dict:
             base = cpu_baseline(w, batch, samples=3, warmup=0, name_stage=varlen, target_s=1.0)
             base.pop("ms_per_step"), base.pop("packets_per_step")
             out["cpu_baseline"] = base
-    del d_pk, d_v, d_offs, d_block, d_gather, d_tot, d_tot_all, h_pk, h_v
+    del d_pk, d_v, d_offs, h_pk, h_v
+    if world > 1:
+        e.comm_destroy()
     e.close()
     torch.cuda.empty_cache()
     return out

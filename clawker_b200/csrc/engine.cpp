@@ -22,7 +22,10 @@
 #include <unordered_map>
 #include <vector>
 
+#include <dlfcn.h>
 #include <unistd.h>
+
+#include <nccl.h>          // types and prototypes only: the library is dlopen()ed by clk_comm_init, never linked
 
 #include "../../include/clawker_gpu.h"
 #include "classify.h"
@@ -98,6 +101,9 @@ struct clk_engine {
     std::map<cudaStream_t, DevBuf> scratch;    // the same for the *_dev entries: one per caller stream, so launches in flight on
                                                // different streams of one engine never share a queue
     DevBuf work_pkts[3], work_offs[3], work_verd[3], scan_sums, scan_pos, scan_total, upd_out, ctr_block;
+    // multi-GPU (clk_comm_*): one NCCL communicator per engine, engine-owned gather buffers
+    ncclComm_t comm = nullptr; int comm_rank = 0, comm_world = 1;
+    DevBuf tot_local, tot_all, met_local, met_all;
     clk_stats stats;
     int loader = LOADER_TMA_SW64;
     int stages = 1;
@@ -122,6 +128,43 @@ int fail(clk_engine *e, int code, const char *fmt, ...)
 #define NEED_GPU(e) do { if ((e)->host_only) return fail((e), CLK_ENOSYS, "engine was created host-only (no CUDA device): classification requires the GPU"); \
                          cudaError_t _d = cudaSetDevice((e)->device); if (_d != cudaSuccess) return fail((e), CLK_EIO, "cudaSetDevice(%d): %s", (e)->device, cudaGetErrorString(_d)); \
                          (void)cudaGetLastError(); /* a stale error left by another library on this thread is not ours to report */ } while (0)
+
+
+// ---- NCCL, loaded on demand --------------------------------------------------------------------------------------
+// libclawker_gpu.so does not link NCCL: a single-GPU host never needs it, and inside a process that already carries
+// an NCCL (PyTorch bundles its own libnccl.so.2) dlopen() by SONAME hands back that very copy, so there are never two.
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+NcclApi &nccl()
+{
+    static NcclApi api; static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = { getenv("CLK_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+        for (const char *n : names) { if (n && *n && (api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break; }
+        if (!api.h) { api.err = std::string("dlopen(libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return; }
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.h, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather))dlsym(api.h, "ncclAllGather");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) { api.err = "libnccl.so.2 lacks an expected symbol"; api.h = nullptr; }
+    });
+    return api;
+}
+void comm_release(clk_engine *e)
+{
+    if (e->comm && nccl().h) nccl().CommDestroy(e->comm);
+    e->comm = nullptr; e->comm_world = 1; e->comm_rank = 0;
+    for (DevBuf *b : { &e->tot_local, &e->tot_all, &e->met_local, &e->met_all }) b->release();
+}
+#define NCCL_TRY(e, call) do { ncclResult_t _r = (call); if (_r != ncclSuccess) return fail((e), CLK_EIO, "%s: %s", #call, nccl().GetErrorString(_r)); } while (0)
 
 struct MapSpec { size_t klen, vlen; };
 const MapSpec kSpecs[CLK_MAP__COUNT] = {
@@ -184,6 +227,42 @@ uint32_t crow_index(clk_engine *e, uint64_t cg)
     return idx;
 }
 
+// The cgroup -> row index only grows while cgroups come and go (every container start brings a new cgroup id), and a
+// metric key carries the row index, so rows cannot simply be renumbered.  When dead rows pile up — cgroups that are in
+// neither container_map nor bypass_map — this reads the metric rows back (they name cgroups by id), keeps the cgroups
+// that are live or still own a metric row, renumbers, and hands the rows back for re-import under the new numbering
+// once the new snapshot is active.  `pending` receives the rows to re-import (empty when nothing was compacted).
+int compact_crows_locked(clk_engine *e, std::vector<clk_metric> &pending, bool &compacted)
+{
+    compacted = false;
+    size_t live_now = 0;
+    for (uint64_t cg : e->crow_cg) if (e->container.count(cg) || e->bypass.count(cg)) live_now++;
+    size_t incoming = 0;
+    for (auto &kv : e->container) if (!e->crow_of.count(kv.first)) incoming++;
+    for (auto &kv : e->bypass) if (!e->crow_of.count(kv.first) && !e->container.count(kv.first)) incoming++;
+    const size_t dead = e->crow_cg.size() - live_now;
+    if (dead < 64 && e->crow_cg.size() + incoming <= 2ull * e->max_containers && e->crow_cg.size() + incoming <= CLK_MAX_CROWS) return CLK_OK;
+    std::set<uint64_t> keep;
+    if (e->published && e->T.m_keys) {                  // which cgroups still own metric rows (old snapshot: old numbering)
+        const uint32_t rows = e->T.m_mask + 2;
+        CUDA_TRY(e, e->ctr_block.ensure((size_t)rows * sizeof(clk_metric)));
+        const char *err = launch_counters_export(e->T, (clk_metric *)e->ctr_block.p, rows, e->stream);
+        if (err) return fail(e, CLK_EIO, "counters export: %s", err);
+        std::vector<clk_metric> host(rows);
+        CUDA_TRY(e, cudaMemcpyAsync(host.data(), e->ctr_block.p, (size_t)rows * sizeof(clk_metric), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+        const uint64_t valid = std::min<uint64_t>(host[0].count, rows - 1);
+        for (uint64_t i = 1; i <= valid; i++) if (host[i].count) { pending.push_back(host[i]); keep.insert(host[i].key.cgroup_id); }
+    }
+    std::vector<uint64_t> order;
+    for (uint64_t cg : e->crow_cg) if (e->container.count(cg) || e->bypass.count(cg) || keep.count(cg)) order.push_back(cg);
+    if (order.size() == e->crow_cg.size()) { pending.clear(); return CLK_OK; }      // nothing to reclaim
+    e->crow_cg = order; e->crow_of.clear();
+    for (size_t i = 0; i < order.size(); i++) e->crow_of[order[i]] = (uint32_t)i;
+    compacted = true;
+    return CLK_OK;
+}
+
 int publish_locked(clk_engine *e)
 {
     NEED_GPU(e);
@@ -193,9 +272,11 @@ int publish_locked(clk_engine *e)
     DevTables T; memset(&T, 0, sizeof T);
     cudaStream_t st = e->stream;
 
-    // ---- cgroup rows (stable indices) -----------------------------------------------------------
-    for (auto &kv : e->container) if (crow_index(e, kv.first) == 0xffffffffu) return fail(e, CLK_E2BIG, "more than %u distinct cgroups", CLK_MAX_CROWS);
-    for (auto &kv : e->bypass)    if (crow_index(e, kv.first) == 0xffffffffu) return fail(e, CLK_E2BIG, "more than %u distinct cgroups", CLK_MAX_CROWS);
+    // ---- cgroup rows (stable indices; dead rows are reclaimed, see compact_crows_locked) ----------
+    std::vector<clk_metric> reimport; bool compacted = false;
+    { int rc = compact_crows_locked(e, reimport, compacted); if (rc) return rc; }
+    for (auto &kv : e->container) if (crow_index(e, kv.first) == 0xffffffffu) return fail(e, CLK_E2BIG, "more than %u distinct cgroups with live metric rows", CLK_MAX_CROWS);
+    for (auto &kv : e->bypass)    if (crow_index(e, kv.first) == 0xffffffffu) return fail(e, CLK_E2BIG, "more than %u distinct cgroups with live metric rows", CLK_MAX_CROWS);
     std::vector<ContRow> crows(e->crow_cg.size());
     for (size_t i = 0; i < crows.size(); i++) {
         ContRow &r = crows[i]; memset(&r, 0, sizeof r);
@@ -415,7 +496,9 @@ int publish_locked(clk_engine *e)
     for (auto &kv : e->container) {
         bool seen = false;
         for (uint32_t i = 0; i < T.n_coredns; i++) seen |= T.coredns_ips[i] == kv.second.coredns_ip;
-        if (!seen && T.n_coredns < 8) T.coredns_ips[T.n_coredns++] = kv.second.coredns_ip;
+        if (seen) continue;
+        if (T.n_coredns >= 8) return fail(e, CLK_E2BIG, "more than 8 distinct coredns_ip values in container_map (DNS answers to a 9th CoreDNS would go unseen)");
+        T.coredns_ips[T.n_coredns++] = kv.second.coredns_ip;
     }
     std::sort(T.coredns_ips, T.coredns_ips + T.n_coredns);
     T.m_keys = (unsigned long long *)e->m_keys.p; T.m_counts = (unsigned long long *)e->m_counts.p;
@@ -429,6 +512,24 @@ int publish_locked(clk_engine *e)
         if (!ep6.empty() && ep6.size() * 32 <= 8192) T.stage_ep6_bytes = (uint32_t)ep6.size() * 32;
     }
     e->T = T; e->active = 1 - e->active; e->published = true; e->dirty = false;
+    if (compacted) {                                    // the metric rows again, keyed by the new row numbers
+        unsigned long long ctr[2] = { 0, 0 };            // [0] increments dropped so far survives the rebuild
+        CUDA_TRY(e, cudaMemcpy(ctr, e->m_dropped.p, 16, cudaMemcpyDeviceToHost));
+        const char *err = launch_counters_clear(e->T, st);
+        if (!err && !reimport.empty()) {
+            std::vector<clk_metric> block(reimport.size() + 1);
+            memset(&block[0], 0, sizeof(clk_metric)); block[0].count = reimport.size();
+            std::copy(reimport.begin(), reimport.end(), block.begin() + 1);
+            CUDA_TRY(e, e->ctr_block.ensure(block.size() * sizeof(clk_metric)));
+            CUDA_TRY(e, cudaMemcpyAsync(e->ctr_block.p, block.data(), block.size() * sizeof(clk_metric), cudaMemcpyHostToDevice, st));
+            DevTables U = e->T; U.m_max = 0xffffffffu;   // these rows were admitted before: the max_entries gate does not apply again
+            err = launch_counters_import(U, (const clk_metric *)e->ctr_block.p, 1, (uint32_t)block.size(), st);
+        }
+        if (err) return fail(e, CLK_EIO, "re-import of the metric rows after cgroup-row compaction: %s", err);
+        CUDA_TRY(e, cudaStreamSynchronize(st));
+        ctr[1] = reimport.size();                        // the key counter the max_entries gate reads
+        CUDA_TRY(e, cudaMemcpy(e->m_dropped.p, ctr, 16, cudaMemcpyHostToDevice));
+    }
     return CLK_OK;
 }
 
@@ -443,6 +544,13 @@ int ensure_published(clk_engine *e)
 // ================================================================================================
 // C ABI
 // ================================================================================================
+// Exception barrier of the C ABI (include/clawker_gpu.h: "no call aborts or throws"): every export is a function-try-block,
+// so a std::bad_alloc / length_error from the host containers becomes CLK_ENOMEM / CLK_EIO instead of unwinding into cgo.
+#define CLK_GUARD_INT(e) catch (const std::bad_alloc &) { return fail((e), CLK_ENOMEM, "out of memory"); } \
+    catch (const std::exception &x) { return fail((e), CLK_EIO, "internal error: %s", x.what()); } catch (...) { return fail((e), CLK_EIO, "internal error"); }
+#define CLK_GUARD_VAL(v) catch (...) { return (v); }
+#define CLK_GUARD_VOID catch (...) { }
+
 extern "C" {
 
 uint32_t clk_abi_version(void) { return CLK_ABI_VERSION; }
@@ -460,7 +568,7 @@ const char *clk_strerror(int code)
 const char *clk_last_error(const clk_engine *e) { return e ? e->err.c_str() : tl_error.c_str(); }
 
 int clk_engine_create(const clk_cfg *cfg, clk_engine **out)
-{
+try {
     if (!out) return fail(nullptr, CLK_EINVAL, "out is NULL");
     *out = nullptr;
     if (cfg && cfg->abi_version != CLK_ABI_VERSION) return fail(nullptr, CLK_EINVAL, "abi_version %u != %u", cfg->abi_version, CLK_ABI_VERSION);
@@ -502,10 +610,10 @@ int clk_engine_create(const clk_cfg *cfg, clk_engine **out)
     }
     *out = e;
     return CLK_OK;
-}
+} CLK_GUARD_INT(nullptr)
 
 void clk_engine_destroy(clk_engine *e)
-{
+try {
     if (!e) return;
     if (!e->host_only) {
         cudaSetDevice(e->device);
@@ -514,17 +622,18 @@ void clk_engine_destroy(clk_engine *e)
         for (DevBuf *b : { &e->m_keys, &e->m_counts, &e->m_dropped, &e->g_keys, &e->g_counts, &e->g_dropped, &e->scan_sums, &e->scan_pos, &e->scan_total, &e->upd_out, &e->ctr_block }) b->release();
         for (int i = 0; i < 3; i++) e->work_rare[i].release();
         for (auto &kv : e->scratch) kv.second.release();
+        comm_release(e);
         for (int i = 0; i < 3; i++) { e->work_pkts[i].release(); e->work_offs[i].release(); e->work_verd[i].release(); if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]); }
         if (e->ev0) cudaEventDestroy(e->ev0);
         if (e->ev1) cudaEventDestroy(e->ev1);
         if (e->stream) cudaStreamDestroy(e->stream);
     }
     delete e;
-}
+} CLK_GUARD_VOID
 
 // ---- map ops ------------------------------------------------------------------------------------
 int clk_map_update(clk_engine *e, int id, const void *key, size_t klen, const void *val, size_t vlen)
-{
+try {
     if (!e || !key || id < 0 || id >= CLK_MAP__COUNT) return fail(e, CLK_EINVAL, "bad map id %d", id);
     if (id == CLK_MAP_METRICS) return fail(e, CLK_EINVAL, "metrics_map is written by the classifier only");
     if (klen != kSpecs[id].klen || (id != CLK_MAP_CIDR && (vlen != kSpecs[id].vlen || !val))) return fail(e, CLK_EINVAL, "map %d: key/value size %zu/%zu, want %zu/%zu", id, klen, vlen, kSpecs[id].klen, kSpecs[id].vlen);
@@ -551,10 +660,10 @@ int clk_map_update(clk_engine *e, int id, const void *key, size_t klen, const vo
     }
     e->dirty = true;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_map_delete(clk_engine *e, int id, const void *key, size_t klen)
-{
+try {
     if (!e || !key || id < 0 || id >= CLK_MAP__COUNT || id == CLK_MAP_METRICS) return fail(e, CLK_EINVAL, "bad map id %d", id);
     if (klen != kSpecs[id].klen) return fail(e, CLK_EINVAL, "map %d: key size %zu, want %zu", id, klen, kSpecs[id].klen);
     std::lock_guard<std::mutex> g(e->mu);
@@ -571,10 +680,10 @@ int clk_map_delete(clk_engine *e, int id, const void *key, size_t klen)
     if (!n) return CLK_ENOENT;                          // ebpf.ErrKeyNotExist: callers treat as success (manager.go:222-231)
     e->dirty = true;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_map_lookup(clk_engine *e, int id, const void *key, size_t klen, void *val, size_t vlen)
-{
+try {
     if (!e || !key || !val || id < 0 || id >= CLK_MAP__COUNT || id == CLK_MAP_METRICS) return fail(e, CLK_EINVAL, "bad map id %d", id);
     if (klen != kSpecs[id].klen || vlen != kSpecs[id].vlen) return fail(e, CLK_EINVAL, "map %d: key/value size", id);
     std::lock_guard<std::mutex> g(e->mu);
@@ -588,10 +697,10 @@ int clk_map_lookup(clk_engine *e, int id, const void *key, size_t klen, void *va
     case CLK_MAP_CIDR:      { clk_cidr c; memcpy(&c, key, sizeof c); auto it = e->cidr.find({ c.addr, c.mask }); if (it == e->cidr.end()) return CLK_ENOENT; *(uint8_t *)val = 1; return CLK_OK; }
     }
     return CLK_EINVAL;
-}
+} CLK_GUARD_INT(e)
 
 int clk_map_count(clk_engine *e, int id, uint32_t *n)
-{
+try {
     if (!e || !n || id < 0 || id >= CLK_MAP__COUNT) return fail(e, CLK_EINVAL, "bad map id %d", id);
     std::lock_guard<std::mutex> g(e->mu);
     switch (id) {
@@ -605,10 +714,10 @@ int clk_map_count(clk_engine *e, int id, uint32_t *n)
     default: return fail(e, CLK_EINVAL, "use clk_counters_read for metrics_map");
     }
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_map_iter(clk_engine *e, int id, void *keys, void *vals, uint32_t cap, uint32_t *n)
-{
+try {
     if (!e || !n || id < 0 || id >= CLK_MAP__COUNT || id == CLK_MAP_METRICS) return fail(e, CLK_EINVAL, "bad map id %d", id);
     std::lock_guard<std::mutex> g(e->mu);
     uint8_t *kp = (uint8_t *)keys, *vp = (uint8_t *)vals; uint32_t i = 0;
@@ -624,10 +733,10 @@ int clk_map_iter(clk_engine *e, int id, void *keys, void *vals, uint32_t cap, ui
     }
     *n = i;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_routes_replace(clk_engine *e, const clk_route *routes, uint32_t n)
-{
+try {
     if (!e || (n && !routes)) return fail(e, CLK_EINVAL, "routes is NULL");
     std::lock_guard<std::mutex> g(e->mu);
     if (n > e->max_routes) return fail(e, CLK_E2BIG, "%u routes > max_entries %u", n, e->max_routes);
@@ -635,18 +744,18 @@ int clk_routes_replace(clk_engine *e, const clk_route *routes, uint32_t n)
     for (uint32_t i = 0; i < n; i++) e->route[((uint64_t)routes[i].domain_hash << 16) | routes[i].dst_port] = routes[i].envoy_port;   // later duplicates win (UpdateAny)
     e->dirty = true;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_dns_update(clk_engine *e, uint32_t ip, uint32_t domain_hash_, uint32_t ttl, uint32_t now)
-{
+try {
     if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
     if (!now) now = (uint32_t)time(nullptr);
     clk_dns_entry en = { domain_hash_, now + ttl };
     return clk_map_update(e, CLK_MAP_DNS_CACHE, &ip, 4, &en, sizeof en);
-}
+} CLK_GUARD_INT(e)
 
 int clk_dns_gc(clk_engine *e, uint32_t now)
-{
+try {
     if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
     if (!now) now = (uint32_t)time(nullptr);
     std::lock_guard<std::mutex> g(e->mu);
@@ -656,21 +765,21 @@ int clk_dns_gc(clk_engine *e, uint32_t now)
     }
     if (cleared) e->dirty = true;
     return cleared;
-}
+} CLK_GUARD_INT(e)
 
 // ---- rules ----------------------------------------------------------------------------------------
-int clk_validate_dst(const char *dst) { return (dst && validate_dst(dst)) ? CLK_OK : CLK_EINVAL; }
-uint32_t clk_domain_hash(const char *domain, size_t len) { return domain_hash(domain ? domain : "", domain ? len : 0); }
-int clk_ip_to_u32(const char *s, uint32_t *out) { uint32_t v = 0; bool ok = s && ip_to_u32(s, &v); if (out) *out = v; return ok ? CLK_OK : CLK_EINVAL; }
+int clk_validate_dst(const char *dst) try { return (dst && validate_dst(dst)) ? CLK_OK : CLK_EINVAL; } CLK_GUARD_INT(nullptr)
+uint32_t clk_domain_hash(const char *domain, size_t len) try { return domain_hash(domain ? domain : "", domain ? len : 0); } CLK_GUARD_VAL(0u)
+int clk_ip_to_u32(const char *s, uint32_t *out) try { uint32_t v = 0; bool ok = s && ip_to_u32(s, &v); if (out) *out = v; return ok ? CLK_OK : CLK_EINVAL; } CLK_GUARD_INT(nullptr)
 int clk_cidr_to_addr_mask(const char *s, uint32_t *addr, uint32_t *mask)
-{
+try {
     uint32_t a = 0, m = 0; bool ok = s && cidr_to_addr_mask(s, &a, &m);
     if (addr) *addr = a; if (mask) *mask = m;
     return ok ? CLK_OK : CLK_EINVAL;
-}
+} CLK_GUARD_INT(nullptr)
 
 int clk_rules_compile(clk_engine *e, const clk_rule *rules, uint32_t n, const clk_ports *ports, uint32_t *n_warnings)
-{
+try {
     if (!e || (n && !rules)) return fail(e, CLK_EINVAL, "rules is NULL");
     std::vector<EgressRule> rs(n);
     for (uint32_t i = 0; i < n; i++) {
@@ -694,10 +803,10 @@ int clk_rules_compile(clk_engine *e, const clk_rule *rules, uint32_t n, const cl
     e->compiled = std::move(c);
     e->dirty = true;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_rules_dump(clk_engine *e, int kind, char *buf, size_t cap)
-{
+try {
     if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
     std::lock_guard<std::mutex> g(e->mu);
     std::string s;
@@ -713,14 +822,14 @@ int clk_rules_dump(clk_engine *e, int kind, char *buf, size_t cap)
     else return fail(e, CLK_EINVAL, "kind %d", kind);
     if (buf && cap) { size_t k = std::min(cap - 1, s.size()); memcpy(buf, s.data(), k); buf[k] = 0; }
     return (int)s.size() + 1;
-}
+} CLK_GUARD_INT(e)
 
 int clk_publish(clk_engine *e)
-{
+try {
     if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
     std::lock_guard<std::mutex> g(e->mu);
     return publish_locked(e);
-}
+} CLK_GUARD_INT(e)
 
 // ---- classification ---------------------------------------------------------------------------------
 static int finish_launch(clk_engine *e, const char *err, const LaunchInfo &li)
@@ -731,7 +840,7 @@ static int finish_launch(clk_engine *e, const char *err, const LaunchInfo &li)
 }
 
 int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, uint64_t n, uint32_t flags, void *d_verdicts, void *stream)
-{
+try {
     if (!e || (n && (!d_pkts || !d_verdicts))) return fail(e, CLK_EINVAL, "NULL buffer");
     if (stride < 64 || stride % 16) return fail(e, CLK_EINVAL, "stride %u: must be >= 64 and a multiple of 16", stride);
     NEED_GPU(e);
@@ -746,10 +855,10 @@ int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, u
                                    (uint32_t *)sc.p + 2, (uint32_t *)sc.p, &li);
     if (!stream) cudaEventRecord(e->ev1, st);
     return finish_launch(e, err, li);
-}
+} CLK_GUARD_INT(e)
 
 int clk_classify_varlen_dev(clk_engine *e, const void *d_pkts, const void *d_offs16, uint64_t n, uint32_t flags, void *d_verdicts, void *stream)
-{
+try {
     if (!e || (n && (!d_pkts || !d_verdicts || !d_offs16))) return fail(e, CLK_EINVAL, "NULL buffer");
     NEED_GPU(e);
     std::lock_guard<std::mutex> g(e->mu);
@@ -762,7 +871,7 @@ int clk_classify_varlen_dev(clk_engine *e, const void *d_pkts, const void *d_off
     const char *err = launch_varlen(e->T, d_pkts, (const uint32_t *)d_offs16, n, flags, (uint32_t *)d_verdicts, st, (uint32_t *)sc.p, &li);
     if (!stream) cudaEventRecord(e->ev1, st);
     return finish_launch(e, err, li);
-}
+} CLK_GUARD_INT(e)
 
 // Host-buffer entry: chunked 3-deep pipeline, each chunk = H2D copy -> kernel -> D2H copy on its own stream.
 static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, uint32_t stride, uint64_t n, uint32_t flags, uint32_t *verdicts)
@@ -813,20 +922,20 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
 }
 
 int clk_classify_slots(clk_engine *e, const uint8_t *pkts, uint32_t stride, uint64_t n, uint32_t flags, uint32_t *verdicts)
-{
+try {
     if (!e || (n && (!pkts || !verdicts))) return fail(e, CLK_EINVAL, "NULL buffer");
     if (stride < 64 || stride % 16) return fail(e, CLK_EINVAL, "stride %u: must be >= 64 and a multiple of 16", stride);
     return classify_host(e, pkts, nullptr, stride, n, flags, verdicts);
-}
+} CLK_GUARD_INT(e)
 
 int clk_classify_varlen(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, uint64_t n, uint32_t flags, uint32_t *verdicts)
-{
+try {
     if (!e || (n && (!pkts || !verdicts || !offs16))) return fail(e, CLK_EINVAL, "NULL buffer");
     return classify_host(e, pkts, offs16, 0, n, flags, verdicts);
-}
+} CLK_GUARD_INT(e)
 
 int clk_classify_events(clk_engine *e, const clk_event *events, uint64_t n, uint32_t flags, uint32_t *verdicts)
-{
+try {
     if (!e || (n && (!events || !verdicts))) return fail(e, CLK_EINVAL, "NULL buffer");
     NEED_GPU(e);
     std::lock_guard<std::mutex> g(e->mu);
@@ -843,11 +952,11 @@ int clk_classify_events(clk_engine *e, const clk_event *events, uint64_t n, uint
     CUDA_TRY(e, cudaMemcpyAsync(verdicts, e->work_verd[0].p, n * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(e, cudaStreamSynchronize(st));
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_dns_answers(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, uint64_t n, const uint32_t *verdicts,
                     clk_dns_update_rec *out, uint64_t cap, uint64_t *n_out, int apply, uint32_t now)
-{
+try {
     if (!e || !n_out || (n && (!pkts || !offs16 || !verdicts))) return fail(e, CLK_EINVAL, "NULL buffer");
     NEED_GPU(e);
     *n_out = 0;
@@ -883,18 +992,18 @@ int clk_dns_answers(clk_engine *e, const uint8_t *pkts, const uint32_t *offs16, 
     if (out) memcpy(out, host_out.data(), std::min<uint64_t>(cap, host_out.size()) * sizeof(clk_dns_update_rec));
     if (apply) for (auto &u : host_out) { int rc = clk_dns_update(e, u.ip, u.domain_hash, u.ttl, now); if (rc && rc != CLK_E2BIG) return rc; }
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 // ---- counters -----------------------------------------------------------------------------------------
 int clk_counters_block_rows(clk_engine *e, uint32_t *rows)
-{
+try {
     if (!e || !rows) return fail(e, CLK_EINVAL, "NULL");
     *rows = e->max_metrics + 1 + 1024;     // header + max_entries (+ slack: the entry cap is enforced without a lock)
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_counters_export(clk_engine *e, void *d_block, void *stream)
-{
+try {
     if (!e || !d_block) return fail(e, CLK_EINVAL, "NULL");
     NEED_GPU(e);
     std::lock_guard<std::mutex> g(e->mu);
@@ -903,35 +1012,37 @@ int clk_counters_export(clk_engine *e, void *d_block, void *stream)
     if (err) return fail(e, CLK_EIO, "counters export: %s", err);
     e->stats.kernel_launches++;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_totals_rows(clk_engine *e, uint32_t *rows)
-{
+try {
     if (!e || !rows) return fail(e, CLK_EINVAL, "NULL");
-    *rows = e->max_containers;
+    *rows = 2 * e->max_containers;      // container_map and bypass_map are separate maps of max_containers rows each
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_totals_export(clk_engine *e, void *d_block, void *stream)
-{
+try {
     if (!e || !d_block) return fail(e, CLK_EINVAL, "NULL");
     NEED_GPU(e);
     std::lock_guard<std::mutex> g(e->mu);
     int rc = ensure_published(e); if (rc) return rc;
-    const char *err = launch_counters_totals(e->T, (clk_total *)d_block, e->max_containers, stream ? (cudaStream_t)stream : e->stream);
+    if (e->T.n_crows > 2 * e->max_containers)
+        return fail(e, CLK_E2BIG, "%u cgroup rows do not fit the %u-row totals block (cgroups that left both maps but still own metric rows: clk_counters_reset reclaims them)", e->T.n_crows, 2 * e->max_containers);
+    const char *err = launch_counters_totals(e->T, (clk_total *)d_block, 2 * e->max_containers, stream ? (cudaStream_t)stream : e->stream);
     if (err) return fail(e, CLK_EIO, "totals export: %s", err);
     e->stats.kernel_launches++;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_totals_merge(clk_engine *e, const void *d_blocks, uint32_t n_blocks, clk_total *out, uint32_t cap, uint32_t *n)
-{
+try {
     if (!e || !d_blocks || !n || (cap && !out)) return fail(e, CLK_EINVAL, "NULL");
     NEED_GPU(e);
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(e, cudaSetDevice(e->device));
     CUDA_TRY(e, cudaDeviceSynchronize());
-    std::vector<clk_total> rows((size_t)n_blocks * e->max_containers);
+    std::vector<clk_total> rows((size_t)n_blocks * 2 * e->max_containers);
     if (!rows.empty()) CUDA_TRY(e, cudaMemcpy(rows.data(), d_blocks, rows.size() * sizeof(clk_total), cudaMemcpyDeviceToHost));
     std::map<uint64_t, clk_total> sum;
     for (const clk_total &r : rows) {
@@ -943,7 +1054,7 @@ int clk_totals_merge(clk_engine *e, const void *d_blocks, uint32_t n_blocks, clk
     uint32_t k = 0;
     for (auto &kv : sum) { if (k >= cap) break; out[k++] = kv.second; }
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 static DevTables global_view(clk_engine *e)
 {
@@ -953,7 +1064,7 @@ static DevTables global_view(clk_engine *e)
 }
 
 int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, void *stream)
-{
+try {
     if (!e || !d_blocks) return fail(e, CLK_EINVAL, "NULL");
     NEED_GPU(e);
     std::lock_guard<std::mutex> g(e->mu);
@@ -970,7 +1081,7 @@ int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, 
     if (err) return fail(e, CLK_EIO, "counters import: %s", err);
     e->stats.kernel_launches += 2;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 static int counters_read_impl(clk_engine *e, bool global, clk_metric *out, uint32_t cap, uint32_t *n)
 {
@@ -997,11 +1108,11 @@ static int counters_read_impl(clk_engine *e, bool global, clk_metric *out, uint3
     return CLK_OK;
 }
 
-int clk_counters_read(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n) { return counters_read_impl(e, false, out, cap, n); }
-int clk_counters_read_global(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n) { return counters_read_impl(e, true, out, cap, n); }
+int clk_counters_read(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n) try { return counters_read_impl(e, false, out, cap, n); } CLK_GUARD_INT(e)
+int clk_counters_read_global(clk_engine *e, clk_metric *out, uint32_t cap, uint32_t *n) try { return counters_read_impl(e, true, out, cap, n); } CLK_GUARD_INT(e)
 
 int clk_counters_reset(clk_engine *e)
-{
+try {
     if (!e) return fail(e, CLK_EINVAL, "NULL");
     NEED_GPU(e);
     std::lock_guard<std::mutex> g(e->mu);
@@ -1009,9 +1120,10 @@ int clk_counters_reset(clk_engine *e)
     const char *err = launch_counters_clear(e->T, e->stream);
     if (err) return fail(e, CLK_EIO, "counters clear: %s", err);
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    for (uint64_t cg : e->crow_cg) if (!e->container.count(cg) && !e->bypass.count(cg)) { e->dirty = true; break; }   // dead rows: the next publish drops them
     e->stats.kernel_launches++;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 // ---- pinned state (the bpffs analogue) ------------------------------------------------
 namespace {
@@ -1036,7 +1148,7 @@ enum { PIN_END = 0, PIN_CONTAINER, PIN_BYPASS, PIN_DNS, PIN_ROUTE, PIN_EP, PIN_E
 }  // namespace
 
 int clk_state_save(clk_engine *e, const char *path)
-{
+try {
     if (!e || !path || !*path) return fail(e, CLK_EINVAL, "NULL");
     PinWriter w;
     {
@@ -1067,10 +1179,10 @@ int clk_state_save(clk_engine *e, const char *path)
     const bool closed = fclose(f) == 0;
     if (!wrote || !closed || rename(tmp.c_str(), path) != 0) { int en = errno; remove(tmp.c_str()); return fail(e, CLK_EIO, "write %s: %s", path, strerror(en)); }
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_state_load(clk_engine *e, const char *path)
-{
+try {
     if (!e || !path || !*path) return fail(e, CLK_EINVAL, "NULL");
     FILE *f = fopen(path, "rb");
     if (!f) return fail(e, errno == ENOENT ? CLK_ENOENT : CLK_EIO, "open %s: %s", path, strerror(errno));
@@ -1119,14 +1231,21 @@ int clk_state_load(clk_engine *e, const char *path)
     if (route.size() > e->max_routes) return fail(e, CLK_E2BIG, "%s: %zu routes > max_entries %u", path, route.size(), e->max_routes);
     if (cidr.size() > e->max_cidrs) return fail(e, CLK_E2BIG, "%s: %zu CIDRs > %u", path, cidr.size(), e->max_cidrs);
     if (endpoint6.size() > 256) return fail(e, CLK_E2BIG, "%s: %zu IPv6 endpoints > 256", path, endpoint6.size());
+    // dns_cache is written on BOTH sides of the file: by the control-plane verbs (gc-dns, sync) into the file, and by this
+    // process in memory (clk_dns_answers(apply) / clk_dns_update — dnsbpf's MapWriter).  The reference's pinned map is one
+    // shared object; here the load merges: a row this process holds that the file lacks, or holds with a later expiry, stays.
+    for (auto &kv : e->dns) {
+        auto it = dns.find(kv.first);
+        if (it == dns.end() || it->second.expire_ts < kv.second.expire_ts) { if (it == dns.end() && dns.size() >= e->max_dns) continue; dns[kv.first] = kv.second; }
+    }
     e->container.swap(container); e->bypass.swap(bypass); e->dns.swap(dns); e->route.swap(route);
     e->endpoint.swap(endpoint); e->endpoint6.swap(endpoint6); e->cidr.swap(cidr); e->compiled = std::move(comp);
     e->dirty = true;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_get_stats(clk_engine *e, clk_stats *out)
-{
+try {
     if (!e || !out) return fail(e, CLK_EINVAL, "NULL");
     std::lock_guard<std::mutex> g(e->mu);
     if (!e->host_only && e->stats.kernel_launches && e->ev0 && cudaEventQuery(e->ev1) == cudaSuccess) {
@@ -1134,25 +1253,123 @@ int clk_get_stats(clk_engine *e, clk_stats *out)
     }
     *out = e->stats;
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
 
 int clk_sync(clk_engine *e)
-{
+try {
     if (!e) return fail(e, CLK_EINVAL, "NULL");
     NEED_GPU(e);
     CUDA_TRY(e, cudaSetDevice(e->device));
     CUDA_TRY(e, cudaDeviceSynchronize());
     return CLK_OK;
-}
+} CLK_GUARD_INT(e)
+
+// ---- multi-GPU: the one collective of the path, behind the C ABI (SURVEY 8(b) clk_allgather_counters, 8(e)) -------------
+// Reference analogue: metrics_map is BPF_MAP_TYPE_PERCPU_HASH (common.h:171-177) and a reader sums the per-CPU values;
+// here every GPU of the host counts on its own and the sum over GPUs is an NCCL all-gather over NVLink + a local sum.
+int clk_comm_unique_id(void *out, size_t cap, size_t *len)
+try {
+    if (!out || cap < sizeof(ncclUniqueId)) return fail(nullptr, CLK_EINVAL, "unique id needs %zu bytes", sizeof(ncclUniqueId));
+    if (!nccl().h) return fail(nullptr, CLK_ENOSYS, "NCCL unavailable: %s", nccl().err.c_str());
+    ncclUniqueId id;
+    NCCL_TRY(nullptr, nccl().GetUniqueId(&id));
+    memcpy(out, &id, sizeof id);
+    if (len) *len = sizeof id;
+    return CLK_OK;
+} CLK_GUARD_INT(nullptr)
+
+int clk_comm_init(clk_engine *e, const void *unique_id, size_t len, int rank, int world)
+try {
+    if (!e || !unique_id || len != sizeof(ncclUniqueId) || world < 1 || rank < 0 || rank >= world) return fail(e, CLK_EINVAL, "bad communicator arguments (id %zu bytes, rank %d of %d)", len, rank, world);
+    NEED_GPU(e);
+    if (!nccl().h) return fail(e, CLK_ENOSYS, "NCCL unavailable: %s", nccl().err.c_str());
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->comm) comm_release(e);
+    ncclUniqueId id; memcpy(&id, unique_id, sizeof id);
+    NCCL_TRY(e, nccl().CommInitRank(&e->comm, world, id, rank));
+    e->comm_rank = rank; e->comm_world = world;
+    return CLK_OK;
+} CLK_GUARD_INT(e)
+
+int clk_comm_destroy(clk_engine *e)
+try {
+    if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    comm_release(e);
+    return CLK_OK;
+} CLK_GUARD_INT(e)
+
+int clk_comm_info(clk_engine *e, int *rank, int *world)
+try {
+    if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
+    std::lock_guard<std::mutex> g(e->mu);
+    if (rank) *rank = e->comm_rank;
+    if (world) *world = e->comm ? e->comm_world : 1;
+    return CLK_OK;
+} CLK_GUARD_INT(e)
+
+// Per batch (enqueue only): dense per-container totals of this GPU's metrics_map -> all-gather of every GPU's block.
+// Without a communicator (single GPU) the gathered view is this GPU's block.
+int clk_allgather_counters(clk_engine *e, void *stream)
+try {
+    if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    const uint32_t rows = 2 * e->max_containers; const size_t blk = (size_t)rows * sizeof(clk_total);
+    const int world = e->comm ? e->comm_world : 1;
+    if (e->T.n_crows > rows) return fail(e, CLK_E2BIG, "%u cgroup rows do not fit the %u-row totals block", e->T.n_crows, rows);
+    CUDA_TRY(e, e->tot_local.ensure(blk)); CUDA_TRY(e, e->tot_all.ensure(blk * world));
+    clk_total *mine = e->comm ? (clk_total *)e->tot_local.p : (clk_total *)e->tot_all.p;
+    const char *err = launch_counters_totals(e->T, mine, rows, st);
+    if (err) return fail(e, CLK_EIO, "totals export: %s", err);
+    e->stats.kernel_launches++;
+    if (e->comm) NCCL_TRY(e, nccl().AllGather(e->tot_local.p, e->tot_all.p, blk, ncclUint8, e->comm, st));
+    return CLK_OK;
+} CLK_GUARD_INT(e)
+
+// The gathered totals summed by cgroup_id, rows sorted by cgroup_id (synchronises the device).
+int clk_totals_read_global(clk_engine *e, clk_total *out, uint32_t cap, uint32_t *n)
+try {
+    if (!e || !n || (cap && !out)) return fail(e, CLK_EINVAL, "NULL");
+    void *blocks; int world;
+    { std::lock_guard<std::mutex> g(e->mu); blocks = e->tot_all.p; world = e->comm ? e->comm_world : 1; }
+    if (!blocks) { *n = 0; return CLK_OK; }
+    return clk_totals_merge(e, blocks, (uint32_t)world, out, cap, n);
+} CLK_GUARD_INT(e)
+
+// On read (enqueue only): per-key merge — compacted export of this GPU's metrics_map -> all-gather -> import into the
+// merged view that clk_counters_read_global returns.
+int clk_allgather_metrics(clk_engine *e, void *stream)
+try {
+    if (!e) return fail(e, CLK_EINVAL, "engine is NULL");
+    NEED_GPU(e);
+    uint32_t rows = 0; void *local, *all; int world;
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        int rc = ensure_published(e); if (rc) return rc;
+        rows = e->max_metrics + 1 + 1024; world = e->comm ? e->comm_world : 1;
+        const size_t blk = (size_t)rows * sizeof(clk_metric);
+        CUDA_TRY(e, e->met_local.ensure(blk)); CUDA_TRY(e, e->met_all.ensure(blk * world));
+        local = e->comm ? e->met_local.p : e->met_all.p; all = e->met_all.p;
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    int rc = clk_counters_export(e, local, st); if (rc) return rc;
+    if (e->comm) NCCL_TRY(e, nccl().AllGather(local, all, (size_t)rows * sizeof(clk_metric), ncclUint8, e->comm, st));
+    return clk_counters_import(e, all, (uint32_t)world, st);
+} CLK_GUARD_INT(e)
 
 // Pinned host memory for packet ingest rings (true DMA for the host-buffer entry points).
 int clk_host_alloc(size_t bytes, void **out)
-{
+try {
     if (!out) return fail(nullptr, CLK_EINVAL, "out is NULL");
     cudaError_t c = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
     if (c != cudaSuccess) return fail(nullptr, CLK_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(c));
     return CLK_OK;
-}
-int clk_host_free(void *p) { if (p) cudaFreeHost(p); return CLK_OK; }
+} CLK_GUARD_INT(nullptr)
+int clk_host_free(void *p) try { if (p) cudaFreeHost(p); return CLK_OK; } CLK_GUARD_INT(nullptr)
 
 }  // extern "C"

@@ -63,12 +63,16 @@ int pack(PcapFile &pf, uint8_t *blob, uint64_t cap_bytes, uint32_t *offs16, uint
 
 }  // namespace
 
+// Exception barrier (see engine.cpp): std::async / std::string can throw; nothing may unwind into the caller.
+#define CLK_GUARD_INT(e) catch (const std::bad_alloc &) { tl_pcap_error = "out of memory"; return CLK_ENOMEM; } \
+    catch (const std::exception &x) { tl_pcap_error = std::string("internal error: ") + x.what(); return CLK_EIO; } catch (...) { tl_pcap_error = "internal error"; return CLK_EIO; }
+
 extern "C" {
 
 const char *clk_pcap_last_error(void) { return tl_pcap_error.c_str(); }
 
 int clk_pcap_pack(const char *path, uint64_t *cursor, uint8_t *blob, uint64_t cap_bytes, uint32_t *offs16, uint64_t cap_frames, uint64_t *n_frames)
-{
+try {
     if (!path || !cursor || !blob || !offs16 || !n_frames) { tl_pcap_error = "NULL"; return CLK_EINVAL; }
     PcapFile pf; int rc = pf.open(path, *cursor);
     if (rc != CLK_OK) return rc;
@@ -76,10 +80,10 @@ int clk_pcap_pack(const char *path, uint64_t *cursor, uint8_t *blob, uint64_t ca
     rc = pack(pf, blob, cap_bytes, offs16, cap_frames, 0, n_frames, &bytes, &eof);
     *cursor = eof ? 0 : (uint64_t)ftello(pf.f);                         // 0 = nothing left to read
     return rc;
-}
+} CLK_GUARD_INT(nullptr)
 
 int clk_classify_pcap(clk_engine *e, const char *path, uint32_t flags, uint32_t *verdicts, uint64_t cap, uint64_t *n)
-{
+try {
     if (!e || !path || !n || (cap && !verdicts)) { tl_pcap_error = "NULL"; return CLK_EINVAL; }
     PcapFile pf; int rc = pf.open(path, 0);
     if (rc != CLK_OK) return rc;
@@ -112,6 +116,6 @@ int clk_classify_pcap(clk_engine *e, const char *path, uint32_t flags, uint32_t 
     release();
     *n = total;                                                         // frames in the file (may exceed cap: verdicts holds the first cap)
     return rc;
-}
+} CLK_GUARD_INT(e)
 
 }  // extern "C"

@@ -92,6 +92,13 @@ def lib() -> C.CDLL:
         "clk_totals_rows": (i32, [vp, C.POINTER(u32)]),
         "clk_totals_export": (i32, [vp, vp, vp]),
         "clk_totals_merge": (i32, [vp, vp, u32, vp, u32, C.POINTER(u32)]),
+        "clk_comm_unique_id": (i32, [vp, sz, C.POINTER(sz)]),
+        "clk_comm_init": (i32, [vp, vp, sz, i32, i32]),
+        "clk_comm_destroy": (i32, [vp]),
+        "clk_comm_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+        "clk_allgather_counters": (i32, [vp, vp]),
+        "clk_totals_read_global": (i32, [vp, vp, u32, C.POINTER(u32)]),
+        "clk_allgather_metrics": (i32, [vp, vp]),
         "clk_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "clk_sync": (i32, [vp]),
         "clk_host_alloc": (i32, [sz, C.POINTER(vp)]),
@@ -110,7 +117,8 @@ EXPORTS = ["clk_abi_version", "clk_strerror", "clk_last_error", "clk_engine_crea
            "clk_cidr_to_addr_mask", "clk_rules_compile", "clk_rules_dump", "clk_publish", "clk_classify_slots",
            "clk_classify_varlen", "clk_classify_slots_dev", "clk_classify_varlen_dev", "clk_classify_events",
            "clk_dns_answers", "clk_counters_read", "clk_counters_read_global", "clk_counters_reset", "clk_counters_block_rows",
-           "clk_counters_export", "clk_counters_import", "clk_totals_rows", "clk_totals_export", "clk_totals_merge", "clk_state_save", "clk_state_load", "clk_pcap_pack", "clk_classify_pcap", "clk_pcap_last_error", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
+           "clk_counters_export", "clk_counters_import", "clk_totals_rows", "clk_totals_export", "clk_totals_merge", "clk_comm_unique_id", "clk_comm_init", "clk_comm_destroy", "clk_comm_info",
+           "clk_allgather_counters", "clk_totals_read_global", "clk_allgather_metrics", "clk_state_save", "clk_state_load", "clk_pcap_pack", "clk_classify_pcap", "clk_pcap_last_error", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
 
 
 def pcap_pack(path: str, cap_bytes: int = 64 << 20, cap_frames: int = 1 << 20):
@@ -377,6 +385,31 @@ class Engine:
         self._ck(self.L.clk_totals_merge(self.h, d_blocks, n_blocks, out.ctypes.data, out.shape[0], C.byref(n)))
         return out[:n.value]
 
+    # multi-GPU: the collective behind the C ABI (NCCL is dlopen()ed by the library)
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(unique_id, len(unique_id))
+        self._ck(self.L.clk_comm_init(self.h, buf, len(unique_id), rank, world))
+
+    def comm_destroy(self):
+        self._ck(self.L.clk_comm_destroy(self.h))
+
+    def allgather_counters(self, stream: int = 0):
+        """Per batch, enqueue only: per-container totals of this GPU -> all-gather of every GPU's block."""
+        self._ck(self.L.clk_allgather_counters(self.h, stream or None))
+
+    def totals_global(self) -> np.ndarray:
+        """The gathered totals summed by cgroup_id (synchronises the device)."""
+        info_w = C.c_int()
+        self._ck(self.L.clk_comm_info(self.h, None, C.byref(info_w)))
+        out = np.zeros(max(1, info_w.value) * self.totals_rows(), dtype=abi.TOTAL_DTYPE)
+        n = C.c_uint32()
+        self._ck(self.L.clk_totals_read_global(self.h, out.ctypes.data, out.shape[0], C.byref(n)))
+        return out[:n.value]
+
+    def allgather_metrics(self, stream: int = 0):
+        """On read, enqueue only: per-key export -> all-gather -> import into the merged view (counters(merged=True))."""
+        self._ck(self.L.clk_allgather_metrics(self.h, stream or None))
+
     def stats(self) -> Stats:
         s = Stats()
         self._ck(self.L.clk_get_stats(self.h, C.byref(s)))
@@ -384,6 +417,15 @@ class Engine:
 
     def sync(self):
         self._ck(self.L.clk_sync(self.h))
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls this and hands the bytes to the other ranks)."""
+    buf, n = C.create_string_buffer(256), C.c_size_t()
+    rc = lib().clk_comm_unique_id(buf, 256, C.byref(n))
+    if rc:
+        raise ClkError(rc, lib().clk_last_error(None).decode())
+    return buf.raw[:n.value]
 
 
 def domain_hash(s: str) -> int:

@@ -16,6 +16,7 @@ import "C"
 import (
 	"errors"
 	"fmt"
+	"strings"
 	"unsafe"
 )
 
@@ -173,6 +174,27 @@ func (e *Engine) RulesCompile(rules []Rule, egressPort, tcpPortBase int) (warnin
 // Publish flips the table epoch: classification sees every change made so far.
 func (e *Engine) Publish() error { return e.err(C.clk_publish(e.h)) }
 
+// RulesDump returns one compiled table as lines (clk_rules_dump): kind 0 zones, 1 server_names, 2 TCP mappings
+// "dst:port:envoy_port", 3 HTTP virtual hosts.
+func (e *Engine) RulesDump(kind int) ([]string, error) {
+	n := C.clk_rules_dump(e.h, C.int(kind), nil, 0)
+	if n < 0 {
+		return nil, e.err(n)
+	}
+	buf := (*C.char)(C.malloc(C.size_t(n)))
+	defer C.free(unsafe.Pointer(buf))
+	if rc := C.clk_rules_dump(e.h, C.int(kind), buf, C.size_t(n)); rc < 0 {
+		return nil, e.err(rc)
+	}
+	var out []string
+	for _, l := range strings.Split(C.GoString(buf), "\n") {
+		if l != "" {
+			out = append(out, l)
+		}
+	}
+	return out, nil
+}
+
 // ClassifySlots classifies n = len(pkts)/stride frames laid out as fixed slots; verdicts must hold n words.
 func (e *Engine) ClassifySlots(pkts []byte, stride int, flags uint32, verdicts []uint32) error {
 	n := len(pkts) / stride
@@ -255,6 +277,46 @@ func (e *Engine) TotalsMerge(dBlocks unsafe.Pointer, nBlocks uint32) ([]Total, e
 }
 
 // StateSave / StateLoad: the pinned state shared with the ebpf-manager verbs (the bpffs analogue).
+// CommUniqueID is ncclGetUniqueId through the library: rank 0 calls it and hands the bytes to the other ranks.
+func CommUniqueID() ([]byte, error) {
+	buf := make([]byte, 256)
+	var n C.size_t
+	if rc := C.clk_comm_unique_id(unsafe.Pointer(&buf[0]), C.size_t(len(buf)), &n); rc != C.CLK_OK {
+		return nil, fmt.Errorf("clk_comm_unique_id: %s", C.GoString(C.clk_last_error(nil)))
+	}
+	return buf[:int(n)], nil
+}
+
+// CommInit joins this engine (one per GPU) to the host's communicator; AllgatherCounters is the per-batch collective.
+func (e *Engine) CommInit(id []byte, rank, world int) error {
+	return e.err(C.clk_comm_init(e.h, unsafe.Pointer(&id[0]), C.size_t(len(id)), C.int(rank), C.int(world)))
+}
+func (e *Engine) CommDestroy() error { return e.err(C.clk_comm_destroy(e.h)) }
+func (e *Engine) AllgatherCounters(stream unsafe.Pointer) error {
+	return e.err(C.clk_allgather_counters(e.h, stream))
+}
+func (e *Engine) AllgatherMetrics(stream unsafe.Pointer) error {
+	return e.err(C.clk_allgather_metrics(e.h, stream))
+}
+
+// TotalsGlobal returns the gathered per-container totals of all GPUs, summed by cgroup id.
+func (e *Engine) TotalsGlobal() ([]Total, error) {
+	rows, err := e.TotalsRows()
+	if err != nil {
+		return nil, err
+	}
+	var world C.int
+	if rc := C.clk_comm_info(e.h, nil, &world); rc != C.CLK_OK {
+		return nil, e.err(rc)
+	}
+	out := make([]Total, int(rows)*int(world))
+	var n C.uint32_t
+	if rc := C.clk_totals_read_global(e.h, (*C.clk_total)(unsafe.Pointer(&out[0])), C.uint32_t(len(out)), &n); rc != C.CLK_OK {
+		return nil, e.err(rc)
+	}
+	return out[:int(n)], nil
+}
+
 func (e *Engine) StateSave(path string) error {
 	p := C.CString(path)
 	defer C.free(unsafe.Pointer(p))

@@ -13,6 +13,8 @@ import "C"
 
 import (
 	"fmt"
+	"strconv"
+	"strings"
 	"unsafe"
 
 	"github.com/schmitthub/clawker/go/clkgpu"
@@ -49,4 +51,34 @@ func CompileRules(e *clkgpu.Engine, rules []EgressRule, ports EnvoyPorts) (warni
 		return warnings, err
 	}
 	return warnings, e.Publish()
+}
+
+// TCPMapping is firewall.TCPMapping (internal/firewall/envoy.go:40-48): one tcp/ssh allow rule and the Envoy listener port it owns.
+type TCPMapping struct {
+	Dst       string
+	DstPort   int
+	EnvoyPort int
+}
+
+// TCPMappings is the reference's firewall.TCPMappings(rules, ports) (internal/firewall/envoy.go:54-83): the mappings the
+// engine derived when the rules were compiled, in rule order (EnvoyPort = TCPPortBase + index).  CompileRules must have run.
+func TCPMappings(e *clkgpu.Engine) ([]TCPMapping, error) {
+	lines, err := e.RulesDump(2)
+	if err != nil {
+		return nil, err
+	}
+	out := make([]TCPMapping, 0, len(lines))
+	for _, l := range lines {
+		f := strings.Split(l, ":")
+		if len(f) != 3 {
+			return nil, fmt.Errorf("malformed mapping %q", l)
+		}
+		dp, err1 := strconv.Atoi(f[1])
+		ep, err2 := strconv.Atoi(f[2])
+		if err1 != nil || err2 != nil {
+			return nil, fmt.Errorf("malformed mapping %q", l)
+		}
+		out = append(out, TCPMapping{Dst: f[0], DstPort: dp, EnvoyPort: ep})
+	}
+	return out, nil
 }

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CLK_ABI_VERSION 2
+#define CLK_ABI_VERSION 3
 
 /* ---- error codes (negative errno style; ENOENT mirrors ebpf.ErrKeyNotExist,
  *      internal/ebpf/manager.go:222-231) ------------------------------------ */
@@ -347,7 +347,7 @@ int clk_counters_export(clk_engine *e, void *d_block, void *stream);
 int clk_counters_import(clk_engine *e, const void *d_blocks, uint32_t n_blocks, void *stream);
 
 /* Per-batch form of the same collective: dense per-container totals of the local table, one
- * clk_total per container_map row (`rows` = max_containers, unused rows zero) in a caller-provided
+ * clk_total per cgroup row (`rows` = 2 x max_containers: container_map and bypass_map rows; unused rows zero) in a caller-provided
  * DEVICE buffer — 32 B per container instead of 24 B per metrics_map row, so it is cheap enough to
  * all-gather after every batch; the per-key merge above then runs only when somebody reads it.
  * clk_totals_merge sums `n_blocks` gathered blocks by cgroup_id into host rows sorted by cgroup_id
@@ -359,6 +359,25 @@ typedef struct clk_total {
 int clk_totals_rows(clk_engine *e, uint32_t *rows);
 int clk_totals_export(clk_engine *e, void *d_block, void *stream);
 int clk_totals_merge(clk_engine *e, const void *d_blocks, uint32_t n_blocks, clk_total *out, uint32_t cap, uint32_t *n);
+
+/* ---- multi-GPU: the one collective of the path ------------------------------------ */
+/* The reference's metrics_map is BPF_MAP_TYPE_PERCPU_HASH (internal/ebpf/bpf/common.h:171-177): every CPU counts
+ * on its own and a reader sums the per-CPU values.  Here every GPU of the host counts on its own (one engine per
+ * GPU, packets sharded by index, tables replicated) and the sum is an NCCL all-gather over NVLink + a local sum.
+ * NCCL is dlopen()ed on first use ("libnccl.so.2", or $CLK_NCCL_LIB) — a single-GPU host never needs it.
+ *   rank 0:      clk_comm_unique_id(id)            -> hand the 128 bytes to the other ranks (any host channel)
+ *   every rank:  clk_comm_init(e, id, 128, rank, world)
+ *   per batch:   clk_classify_*_dev(...); clk_allgather_counters(e, side_stream)       (enqueue only)
+ *   reader:      clk_totals_read_global(...)  — per-container ALLOW / DENY / BYPASS totals of all GPUs
+ *                clk_allgather_metrics(e, stream); clk_counters_read_global(...) — the per-key merged map
+ * Without a communicator the same calls work on one GPU (the gathered view is the local block). */
+int clk_comm_unique_id(void *out, size_t cap, size_t *len);
+int clk_comm_init(clk_engine *e, const void *unique_id, size_t len, int rank, int world);
+int clk_comm_destroy(clk_engine *e);
+int clk_comm_info(clk_engine *e, int *rank, int *world);
+int clk_allgather_counters(clk_engine *e, void *stream);
+int clk_totals_read_global(clk_engine *e, clk_total *out, uint32_t cap, uint32_t *n);
+int clk_allgather_metrics(clk_engine *e, void *stream);
 
 /* ---- introspection for benches ------------------------------------------------ */
 typedef struct clk_stats {

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, f"declared in the header but not exported: {missing}"
     assert declared == set(engine.EXPORTS), sorted(declared ^ set(engine.EXPORTS))
-    assert L.clk_abi_version() == 2
+    assert L.clk_abi_version() == 3
 
 
 def test_struct_sizes_match_reference_layouts():

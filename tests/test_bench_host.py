@@ -129,7 +129,14 @@ class _FakeEngine:
 
     def _launch(self, *a):
         self.st.kernel_launches += 1
-    classify_slots_dev = classify_varlen_dev = totals_export = counters_export = _launch
+    classify_slots_dev = classify_varlen_dev = totals_export = counters_export = allgather_counters = _launch
+
+    def comm_init(self, uid, rank, world): self.world = world
+    def comm_destroy(self): pass
+    def allgather_metrics(self, stream=0): pass
+
+    def totals_global(self):
+        return self.totals_merge(0, getattr(self, "world", 1))
 
     def counters_import(self, *a): pass
     def counters_reset(self): pass
@@ -169,8 +176,9 @@ def _dry_run(monkeypatch, capsys, world, workload):
     monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch, "device", lambda *a, **k: cpu)
-    for name in ("init_process_group", "barrier", "destroy_process_group", "all_gather_into_tensor", "all_reduce"):
+    for name in ("init_process_group", "barrier", "destroy_process_group", "all_gather_into_tensor", "all_reduce", "broadcast_object_list"):
         monkeypatch.setattr(dist, name, lambda *a, **k: None)
+    monkeypatch.setattr(engine, "comm_unique_id", lambda: b"\0" * 128)
     monkeypatch.setattr(engine, "Engine", _FakeEngine)
     monkeypatch.setattr(engine, "pinned_empty", lambda n: np.empty(n, dtype=np.uint8))
     monkeypatch.setitem(bench.WORKLOADS[workload], "gen", 4096)

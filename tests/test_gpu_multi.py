@@ -28,7 +28,18 @@ def _worker(rank, world, port, q):
     tg.enqueue()                                              # per-batch form: dense per-container totals
     totals = tg.read()
     sharding.allgather_counters(e)                            # on-read form: per-key merge
-    q.put((rank, lo, hi, verd, e.counters(merged=True), e.counters(), totals))
+    merged_torch = e.counters(merged=True)
+    # the same two collectives behind the C ABI (clk_comm_init / clk_allgather_counters / clk_allgather_metrics): what a Go host calls
+    from clawker_b200 import engine as eng
+    ids = [eng.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    e.comm_init(ids[0], rank, world)
+    e.allgather_counters()
+    totals_abi = e.totals_global()
+    e.allgather_metrics()
+    merged_abi = e.counters(merged=True)
+    e.comm_destroy()
+    q.put((rank, lo, hi, verd, merged_torch, e.counters(), totals, totals_abi, merged_abi))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,8 +69,11 @@ def test_two_gpu_shards_and_nccl_counter_allgather():
     want_v, want_m = oracle.Oracle("port").load(oracle_tables(w)).classify(pk)
     assert np.array_equal(np.concatenate([r[3] for r in res]), want_v)
     want_t = sharding.merge_totals(sharding.totals_of(want_m, 256))
-    for rank, lo, hi, verd, merged, local, totals in res:
+    for rank, lo, hi, verd, merged, local, totals, totals_abi, merged_abi in res:
         assert_same_metrics(merged, want_m, f"rank {rank} merged")
+        assert_same_metrics(merged_abi, want_m, f"rank {rank} merged through clk_allgather_metrics")
+        totals_abi = totals_abi[totals_abi["count"].sum(axis=1) > 0]
+        assert np.array_equal(totals_abi, want_t), f"rank {rank} totals through clk_allgather_counters"
         totals = totals[totals["count"].sum(axis=1) > 0]                     # containers without traffic have all-zero rows
         assert np.array_equal(totals, want_t), f"rank {rank} totals"
         assert int(local["count"].sum()) < int(merged["count"].sum())
