@@ -71,6 +71,8 @@ EVENT_DTYPE = np.dtype([("cgroup_id", "<u8"), ("uid", "<u4"), ("so_mark", "<u4")
 METRIC_DTYPE = np.dtype([("cgroup_id", "<u8"), ("domain_hash", "<u4"), ("dst_port", "<u2"), ("action", "u1"),
                          ("_pad", "u1"), ("count", "<u8")])
 TOTAL_DTYPE = np.dtype([("cgroup_id", "<u8"), ("count", "<u8", (3,))])           # clk_total: ALLOW, DENY, BYPASS
+HDR16_DTYPE = np.dtype([("src", "<u4"), ("dst", "<u4"), ("sport", "<u2"), ("dport", "<u2"), ("proto", "u1"), ("kind", "u1"), ("_pad", "<u2")])   # clk_hdr16
+assert HDR16_DTYPE.itemsize == 16
 DNSUPD_DTYPE = np.dtype([("ip", "<u4"), ("domain_hash", "<u4"), ("ttl", "<u4"), ("packet", "<u4")])
 assert EVENT_DTYPE.itemsize == 40 and METRIC_DTYPE.itemsize == 24 and DNSUPD_DTYPE.itemsize == 16 and TOTAL_DTYPE.itemsize == 32
 

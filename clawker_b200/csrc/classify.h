@@ -17,6 +17,8 @@ const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride
 uint32_t varlen_rest_cap(unsigned long long n);
 const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n, uint32_t flags,
                           uint32_t *d_verdicts, cudaStream_t st, uint32_t *rest_q, LaunchInfo *info);
+const char *launch_hdr16(const DevTables &T, const void *d_recs, const void *d_aux, unsigned long long n, uint32_t flags, uint32_t *d_verdicts,
+                         cudaStream_t st, LaunchInfo *info);
 const char *launch_events(const DevTables &T, const clk_event *d_ev, unsigned long long n, uint32_t flags, uint32_t *d_verdicts,
                           cudaStream_t st, LaunchInfo *info);
 const char *launch_dns_extract(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n,

@@ -934,6 +934,75 @@ try {
     return classify_host(e, pkts, offs16, 0, n, flags, verdicts);
 } CLK_GUARD_INT(e)
 
+// ---- compact ingest ------------------------------------------------------------------------------------------------
+int clk_pack_hdr16(const uint8_t *pkts, uint32_t stride, uint64_t n, clk_hdr16 *out, uint8_t *aux, uint64_t aux_cap, uint64_t *n_aux)
+try {
+    if ((n && (!pkts || !out)) || !n_aux || stride < 64) return fail(nullptr, CLK_EINVAL, "NULL buffer or stride < 64");
+    uint64_t na = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *p = pkts + i * stride;
+        clk_hdr16 r; memset(&r, 0, sizeof r);
+        const bool ipv4 = p[12] == 0x08 && p[13] == 0x00, ipv6 = p[12] == 0x86 && p[13] == 0xDD;
+        if (ipv4 && p[14] == 0x45 && ((p[20] & 0x1f) | p[21]) == 0) {          // IHL 5, fragment offset 0 (same test as fast_classify)
+            r.kind = CLK_HDR_IPV4; r.proto = p[23];
+            memcpy(&r.src, p + 26, 4); memcpy(&r.dst, p + 30, 4);
+            r.sport = (uint16_t)((p[34] << 8) | p[35]); r.dport = (uint16_t)((p[36] << 8) | p[37]);
+        } else if (!ipv4 && !ipv6) {
+            r.kind = CLK_HDR_NONE;
+        } else {
+            if (!aux || na >= aux_cap) return fail(nullptr, CLK_E2BIG, "aux holds %llu slots, more frames need one", (unsigned long long)aux_cap);
+            if (na > 0xffffffffull) return fail(nullptr, CLK_E2BIG, "more than 2^32 aux slots");
+            memcpy(aux + na * 64, p, 64);
+            r.kind = CLK_HDR_AUX; r.src = (uint32_t)na++;
+        }
+        out[i] = r;
+    }
+    *n_aux = na;
+    return CLK_OK;
+} CLK_GUARD_INT(nullptr)
+
+int clk_classify_hdr16_dev(clk_engine *e, const void *d_recs, uint64_t n, const void *d_aux, uint32_t flags, void *d_verdicts, void *stream)
+try {
+    if (!e || (n && (!d_recs || !d_verdicts))) return fail(e, CLK_EINVAL, "NULL buffer");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    LaunchInfo li = { 0, 0, 0, 0 };
+    const char *err = launch_hdr16(e->T, d_recs, d_aux, n, flags, (uint32_t *)d_verdicts, stream ? (cudaStream_t)stream : e->stream, &li);
+    return finish_launch(e, err, li);
+} CLK_GUARD_INT(e)
+
+int clk_classify_hdr16(clk_engine *e, const clk_hdr16 *recs, uint64_t n, const uint8_t *aux, uint64_t n_aux, uint32_t flags, uint32_t *verdicts)
+try {
+    if (!e || (n && (!recs || !verdicts)) || (n_aux && !aux)) return fail(e, CLK_EINVAL, "NULL buffer");
+    NEED_GPU(e);
+    std::lock_guard<std::mutex> g(e->mu);
+    int rc = ensure_published(e); if (rc) return rc;
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    for (int s = 0; s < 3; s++) CUDA_TRY(e, cudaStreamSynchronize(e->pipe[s]));
+    if (n_aux) {                                              // the few whole frames first, once
+        CUDA_TRY(e, e->work_offs[0].ensure(n_aux * 64));
+        CUDA_TRY(e, cudaMemcpyAsync(e->work_offs[0].p, aux, n_aux * 64, cudaMemcpyHostToDevice, e->pipe[0]));
+        CUDA_TRY(e, cudaStreamSynchronize(e->pipe[0]));
+    }
+    const uint64_t chunk = e->chunk_pkts * 2;
+    uint64_t done = 0; int k = 0;
+    while (done < n) {
+        const uint64_t cnt = std::min<uint64_t>(chunk, n - done);
+        const int s = k % 3; cudaStream_t st = e->pipe[s];
+        CUDA_TRY(e, cudaStreamSynchronize(st));
+        CUDA_TRY(e, e->work_pkts[s].ensure(cnt * sizeof(clk_hdr16))); CUDA_TRY(e, e->work_verd[s].ensure(cnt * 4));
+        CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, recs + done, cnt * sizeof(clk_hdr16), cudaMemcpyHostToDevice, st));
+        LaunchInfo li = { 0, 0, 0, 0 };
+        const char *err = launch_hdr16(e->T, e->work_pkts[s].p, n_aux ? e->work_offs[0].p : nullptr, cnt, flags, (uint32_t *)e->work_verd[s].p, st, &li);
+        rc = finish_launch(e, err, li); if (rc) return rc;
+        CUDA_TRY(e, cudaMemcpyAsync(verdicts + done, e->work_verd[s].p, cnt * 4, cudaMemcpyDeviceToHost, st));
+        done += cnt; k++;
+    }
+    for (int s = 0; s < 3; s++) CUDA_TRY(e, cudaStreamSynchronize(e->pipe[s]));
+    return CLK_OK;
+} CLK_GUARD_INT(e)
+
 int clk_classify_events(clk_engine *e, const clk_event *events, uint64_t n, uint32_t flags, uint32_t *verdicts)
 try {
     if (!e || (n && (!events || !verdicts))) return fail(e, CLK_EINVAL, "NULL buffer");

@@ -77,6 +77,9 @@ def lib() -> C.CDLL:
         "clk_classify_slots_dev": (i32, [vp, vp, u32, u64, u32, vp, vp]),
         "clk_classify_varlen_dev": (i32, [vp, vp, vp, u64, u32, vp, vp]),
         "clk_classify_events": (i32, [vp, vp, u64, u32, vp]),
+        "clk_pack_hdr16": (i32, [vp, u32, u64, vp, vp, u64, C.POINTER(u64)]),
+        "clk_classify_hdr16": (i32, [vp, vp, u64, vp, u64, u32, vp]),
+        "clk_classify_hdr16_dev": (i32, [vp, vp, u64, vp, u32, vp, vp]),
         "clk_dns_answers": (i32, [vp, vp, vp, u64, vp, vp, u64, C.POINTER(u64), i32, u32]),
         "clk_counters_read": (i32, [vp, vp, u32, C.POINTER(u32)]),
         "clk_counters_read_global": (i32, [vp, vp, u32, C.POINTER(u32)]),
@@ -115,7 +118,7 @@ EXPORTS = ["clk_abi_version", "clk_strerror", "clk_last_error", "clk_engine_crea
            "clk_map_update", "clk_map_delete", "clk_map_lookup", "clk_map_iter", "clk_map_count", "clk_routes_replace",
            "clk_dns_update", "clk_dns_gc", "clk_validate_dst", "clk_domain_hash", "clk_ip_to_u32",
            "clk_cidr_to_addr_mask", "clk_rules_compile", "clk_rules_dump", "clk_publish", "clk_classify_slots",
-           "clk_classify_varlen", "clk_classify_slots_dev", "clk_classify_varlen_dev", "clk_classify_events",
+           "clk_classify_varlen", "clk_classify_slots_dev", "clk_classify_varlen_dev", "clk_classify_events", "clk_pack_hdr16", "clk_classify_hdr16", "clk_classify_hdr16_dev",
            "clk_dns_answers", "clk_counters_read", "clk_counters_read_global", "clk_counters_reset", "clk_counters_block_rows",
            "clk_counters_export", "clk_counters_import", "clk_totals_rows", "clk_totals_export", "clk_totals_merge", "clk_comm_unique_id", "clk_comm_init", "clk_comm_destroy", "clk_comm_info",
            "clk_allgather_counters", "clk_totals_read_global", "clk_allgather_metrics", "clk_state_save", "clk_state_load", "clk_pcap_pack", "clk_classify_pcap", "clk_pcap_last_error", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
@@ -326,6 +329,17 @@ class Engine:
     def classify_varlen_dev(self, d_pkts: int, d_offs16: int, n: int, flags: int, d_verdicts: int, stream: int = 0):
         self._ck(self.L.clk_classify_varlen_dev(self.h, d_pkts, d_offs16, n, flags, d_verdicts, stream or None))
 
+    def classify_hdr16(self, recs: np.ndarray, aux: np.ndarray | None = None, flags: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        """Compact ingest records (abi.HDR16_DTYPE, 16 B per frame) + the whole frames they point at (aux, 64 B slots)."""
+        n = recs.shape[0]
+        n_aux = 0 if aux is None else aux.size // 64
+        verd = out if out is not None else np.empty(n, dtype=np.uint32)
+        self._ck(self.L.clk_classify_hdr16(self.h, recs.ctypes.data, n, aux.ctypes.data if n_aux else None, n_aux, flags, verd.ctypes.data))
+        return verd
+
+    def classify_hdr16_dev(self, d_recs: int, n: int, d_aux: int, flags: int, d_verdicts: int, stream: int = 0):
+        self._ck(self.L.clk_classify_hdr16_dev(self.h, d_recs, n, d_aux or None, flags, d_verdicts, stream or None))
+
     def classify_events(self, events: np.ndarray, flags: int = 0) -> np.ndarray:
         events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
         verd = np.empty(events.size, dtype=np.uint32)
@@ -417,6 +431,23 @@ class Engine:
 
     def sync(self):
         self._ck(self.L.clk_sync(self.h))
+
+
+def pack_hdr16(pkts: np.ndarray, stride: int = 64, pinned: bool = False):
+    """clk_pack_hdr16: slot-layout frames -> (records[n] of abi.HDR16_DTYPE, aux bytes [n_aux * 64])."""
+    pkts = np.ascontiguousarray(pkts, dtype=np.uint8)
+    n = pkts.size // stride
+    alloc = (lambda nb: pinned_empty(nb)) if pinned else (lambda nb: np.empty(nb, dtype=np.uint8))
+    recs = alloc(max(1, n) * 16)[: n * 16].view(abi.HDR16_DTYPE)
+    cap = max(1, n // 8 + 1024)
+    while True:
+        aux, n_aux = alloc(cap * 64), C.c_uint64()
+        rc = lib().clk_pack_hdr16(pkts.ctypes.data, stride, n, recs.ctypes.data, aux.ctypes.data, cap, C.byref(n_aux))
+        if rc == 0:
+            return recs, aux[: n_aux.value * 64]
+        if rc != abi.E2BIG or cap >= n:
+            raise ClkError(rc, lib().clk_last_error(None).decode())
+        cap = n
 
 
 def comm_unique_id() -> bytes:

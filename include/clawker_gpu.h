@@ -314,6 +314,33 @@ int clk_classify_slots_dev(clk_engine *e, const void *d_pkts, uint32_t stride, u
 int clk_classify_varlen_dev(clk_engine *e, const void *d_pkts, const void *d_offs16, uint64_t n,
                             uint32_t flags, void *d_verdicts, void *stream);
 
+/* ---- compact ingest (16 bytes per frame over the host link instead of the frame) ---------------- */
+/* What the decision (clawker.c:69-240 through common.h:256-451) reads of an IPv4 header-only frame: the two
+ * addresses, the two ports, the protocol.  A capture front end emits one clk_hdr16 per frame; frames the record
+ * cannot express (IPv6, IPv4 options, later fragments, runts) keep their first 64 bytes in a side array `aux`
+ * and the record points at them, so verdicts are bit-identical to clk_classify_slots on the same frames.  No name
+ * stage on this path (there is no payload). */
+#define CLK_HDR_IPV4 0u       /* Ethernet II / IPv4, IHL 5, first fragment: the fields below are the frame   */
+#define CLK_HDR_NONE 1u       /* no socket event (not IP): verdict word 0                                    */
+#define CLK_HDR_AUX  2u       /* src = index of this frame's 64-byte slot in `aux`                           */
+typedef struct clk_hdr16 {
+    uint32_t src, dst;        /* network order bytes loaded as native u32 (types.go:86-96)                   */
+    uint16_t sport, dport;    /* host order; 0 for protocols without ports                                  */
+    uint8_t  proto;           /* IPv4 protocol                                                               */
+    uint8_t  kind;            /* CLK_HDR_*                                                                   */
+    uint16_t _pad;
+} clk_hdr16;                  /* 16 B */
+/* Host-side front end: `n` frames (slot layout, stride >= 64) -> records (+ aux slots).  *n_aux = slots used;
+ * CLK_E2BIG when aux_cap slots do not suffice. */
+int clk_pack_hdr16(const uint8_t *pkts, uint32_t stride, uint64_t n, clk_hdr16 *out,
+                   uint8_t *aux, uint64_t aux_cap, uint64_t *n_aux);
+/* HOST pointers: chunked H2D / kernel / D2H pipeline like clk_classify_slots.  aux may be NULL when n_aux == 0. */
+int clk_classify_hdr16(clk_engine *e, const clk_hdr16 *recs, uint64_t n, const uint8_t *aux, uint64_t n_aux,
+                       uint32_t flags, uint32_t *verdicts);
+/* DEVICE pointers, enqueue only. */
+int clk_classify_hdr16_dev(clk_engine *e, const void *d_recs, uint64_t n, const void *d_aux,
+                           uint32_t flags, void *d_verdicts, void *stream);
+
 /* Event-level entry: exactly the reference hooks' semantics on pre-parsed events
  * (clawker.c:69-240 with common.h:256-451).  Host pointers. */
 int clk_classify_events(clk_engine *e, const clk_event *events, uint64_t n, uint32_t flags,
