@@ -822,24 +822,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel 1b: variable-length captures with the name stage (BASELINE config 3, the north-star workload)
+// kernels 1b: variable-length captures with the name stage (BASELINE config 3, the north-star workload)
 // ------------------------------------------------------------------------------------------------
-// The frames of consecutive packets are contiguous in the blob, so a CTA stages the whole byte span of a CHUNK of
-// kThreads packets into shared memory with ONE bulk TMA copy (cp.async.bulk, double-buffered: the span of the next
-// chunk lands while this one is classified) and every byte the kernel looks at afterwards — header words and
-// payload parsers alike — is read from shared memory.  DRAM sees each frame exactly once.
-//
-// Phase A (one thread per packet, all lanes converged): the predicated L3/L4 ladder of the slot kernel on the
-// staged header words; it also says what payload work is left (nm).  Packets that need payload work are NOT parsed
-// in place — a byte-serial parser with a few lanes active would dominate the kernel — their thread indices are
-// compacted into per-type CTA lists.  Phase B: the lists are cut into 32-entry units which the warps of the CTA
-// share out, so a warp runs ONE parser (DNS question / DNS-over-TCP / ClientHello / DNS answer / HTTP request) with
-// its lanes full.  Frames the fast ladder does not cover (IPv6, IP options, runts) and chunks whose span exceeds the
-// stage (jumbo frames) are marked with CLK_W_REST in the verdict array and queued for k_varlen_rest, which runs the
-// generic path on them from global memory.
-#define VC_LISTS 5                  // NM_DNSQ .. NM_HTTP (list k-1 holds the threads whose packets need work k)
-#define CLK_W_REST 0xffffffffu      // not a verdict word (bits [1:0] == 3): "k_varlen_rest owes this packet"
-
 template <class P>
 __device__ __forceinline__ void payload_window(P pk, uint32_t avail, bool tcp, uint32_t &po, uint32_t &pl)
 {
@@ -850,187 +834,189 @@ __device__ __forceinline__ void payload_window(P pk, uint32_t avail, bool tcp, u
     else if (34 + 13 <= avail) { uint32_t doff = (gb(pk + 46u) >> 4) * 4; po = 34 + doff; if (doff >= 20 && po <= end) pl = end - po; }
 }
 
-// One unit of phase B: every lane of `mask` holds a packet of the SAME work type and calls together.
-template <class P>
-__device__ __noinline__ uint32_t name_work(const DevTables &T, P pk, uint32_t avail, uint32_t type, uint32_t word, unsigned mask)
+// Measured on B200 (profiles/r02_varlen_notes.md): a fused kernel that holds the header ladder and every payload
+// parser executes ~100 KB of SASS from warps in different phases — far more than the 32 KB L1.5 instruction cache —
+// and stalls on instruction fetch (no_instruction 53 % of warp stalls); a CTA that stages chunks in shared memory and
+// runs the parsers between barriers pays every long-latency event of any warp at the next barrier.  So the work is cut
+// BY ROLE into kernels whose code is small and whose warps all run the same thing:
+//   k_varlen_head     every packet: the header ladder straight from global memory (three 16-byte loads per packet, no
+//                     CTA barrier in the loop), verdicts of packets that need nothing else, metrics; packets that need
+//                     payload work are appended — 32 at a time per warp and type, through shared-memory queues — to one
+//                     global list PER WORK TYPE {index, phase-A word, frame offset, frame length};
+//   k_name_list<type> one parser per launch (DNS question / DNS-over-TCP / ClientHello / DNS answer / HTTP request):
+//                     a warp takes 32 list entries, so its lanes are full and run the same code in lock step;
+//   k_generic_list    the frames the fast ladder does not cover (IPv6, IP options, runts): the generic path.
+// A batch is cut into slices so that the lists stay bounded (VL_SLICE packets); everything is enqueued on one stream.
+#define VW_LISTS 6             // 0 generic, then NM_DNSQ .. NM_HTTP
+#define VW_QCAP 32             // a warp's queue is flushed (wholly) before it would overflow, and when it is full
+
+struct NameEnt { uint32_t idx, word, o16, units; };        // 16 B: packet index, phase-A word, frame offset and length in 16-byte units
+
+template <int kWarps, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks) k_varlen_head(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts,
+                                                                         const uint32_t *__restrict__ offs16, uint32_t first, uint32_t n,
+                                                                         uint32_t flags, uint32_t *__restrict__ verdicts,
+                                                                         uint4 *__restrict__ ents, uint32_t *__restrict__ cnt, uint32_t cap)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const SmemLayout L = smem_layout(T, 0, kWarps * VW_LISTS * VW_QCAP * 16, 0, MSLOTS, kWarps);
+    Tabs tb; MetricAgg ag;
+    cta_prologue<false>(T, smem, L, 0, tb, ag);
+    __syncthreads();
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint4 *queue = (uint4 *)(smem + L.queue) + warp * (VW_LISTS * VW_QCAP);
+    const uint32_t n_tiles = (n + 31u) >> 5;
+    const uint32_t gw = blockIdx.x * kWarps + warp, W = gridDim.x * kWarps;
+    const bool do_metrics = !(flags & CLK_F_NO_METRICS);
+    uint32_t qn[VW_LISTS];
+    #pragma unroll
+    for (int k = 0; k < VW_LISTS; k++) qn[k] = 0;
+
+    // the whole queue k of this warp -> global list k: one atomic, one coalesced store of 16-byte entries
+    auto flush = [&](int k) {
+        const uint32_t take = qn[k];
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cnt[k], take);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < take && base + lane < cap) ents[(size_t)k * cap + base + lane] = queue[k * VW_QCAP + lane];
+        qn[k] = 0;
+        __syncwarp();
+    };
+
+    // Software pipeline, two tiles deep: while tile t is classified, the header words of tile t + W and the offsets of
+    // tile t + 2W are in flight (a warp keeps ~3 KB of loads outstanding; 16 warps cover the DRAM latency of an SM).
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    uint32_t t = gw;
+    uint32_t o0 = 0, o1 = 0, o0n = 0, o1n = 0, w3 = 0; uint4 q1 = z4, q2 = z4;
+    if (t < n_tiles) { const uint32_t i = (t << 5) + lane; if (i < n) { o0 = __ldg(&offs16[first + i]); o1 = __ldg(&offs16[first + i + 1]); } }
+    if (t + W < n_tiles) { const uint32_t i = ((t + W) << 5) + lane; if (i < n) { o0n = __ldg(&offs16[first + i]); o1n = __ldg(&offs16[first + i + 1]); } }
+    if (t < n_tiles && (o1 - o0) >= 4u) {
+        const uint8_t *pk = pkts + (unsigned long long)o0 * 16ull;
+        w3 = __ldg((const uint32_t *)(pk + 12)); q1 = __ldg((const uint4 *)(pk + 16)); q2 = __ldg((const uint4 *)(pk + 32));
+    }
+    for (; t < n_tiles; t += W) {
+        const uint32_t i = (t << 5) + lane;
+        // next tile's header words, the tile after's offsets
+        uint32_t w3n = 0, o0f = 0, o1f = 0; uint4 q1n = z4, q2n = z4;
+        if (t + W < n_tiles && (o1n - o0n) >= 4u) {
+            const uint8_t *pk = pkts + (unsigned long long)o0n * 16ull;
+            w3n = __ldg((const uint32_t *)(pk + 12)); q1n = __ldg((const uint4 *)(pk + 16)); q2n = __ldg((const uint4 *)(pk + 32));
+        }
+        if (t + 2 * W < n_tiles) { const uint32_t i2 = ((t + 2 * W) << 5) + lane; if (i2 < n) { o0f = __ldg(&offs16[first + i2]); o1f = __ldg(&offs16[first + i2 + 1]); } }
+
+        bool hm = false; unsigned long long mk = 0; uint32_t w = 0, kind = 0xffu;   // kind: list to join, 0xff = done here
+        if (i < n) {
+            const uint32_t avail = (o1 - o0) * 16u;
+            kind = 0;
+            if (avail >= 64) {
+                uint32_t nm;
+                if (fast_classify<true>(T, tb, w3, q1, q2.x, q2.y, q2.w, avail, flags, w, hm, mk, nm)) kind = nm == NM_NONE ? 0xffu : nm;
+            }
+            if (kind == 0xffu) stg_stream(&verdicts[first + i], w);
+        }
+        if (do_metrics) metric_warp_emit(T, ag, hm, mk);
+        #pragma unroll
+        for (int k = 0; k < VW_LISTS; k++) {
+            if (k == (int)NM_HTTP) continue;                   // filled by the ClientHello kernel, not here
+            const unsigned m = __ballot_sync(0xffffffffu, kind == (uint32_t)k);
+            if (m) {
+                const uint32_t c = __popc(m);
+                if (qn[k] + c > VW_QCAP) flush(k);
+                if (kind == (uint32_t)k) queue[k * VW_QCAP + qn[k] + __popc(m & ((1u << lane) - 1u))] = make_uint4(first + i, w, o0, o1 - o0);
+                qn[k] += c;
+                __syncwarp();
+                if (qn[k] == VW_QCAP) flush(k);
+            }
+        }
+        o0 = o0n; o1 = o1n; w3 = w3n; q1 = q1n; q2 = q2n; o0n = o0f; o1n = o1f;
+    }
+    #pragma unroll
+    for (int k = 0; k < VW_LISTS; k++) if (qn[k]) flush(k);
+    if (do_metrics) metric_cta_flush(T, ag);
+}
+
+// One parser per instantiation.  Every lane of `mask` holds a packet of work type kType and calls together.
+template <int kType>
+__device__ __forceinline__ uint32_t name_work_t(const DevTables &T, const uint8_t *pk, uint32_t avail, uint32_t word, unsigned mask)
 {
     uint32_t po, pl;
-    if (type == NM_DNSA) {
+    if (kType == (int)NM_DNSA) {
         uint32_t end = 14 + gbe16(pk + 16u); if (end > avail) end = avail;
         const bool has = 42 <= end;
         uint32_t nv, nupd = dns_answer_updates(T, pk + 42u, has ? end - 42 : 0u, 0, nullptr, 0, 0, &nv, mask);
         return has ? (nv << 4) | (nupd << 27) : 0u;
     }
-    payload_window(pk, avail, type != NM_DNSQ, po, pl);
+    payload_window(pk, avail, kType != (int)NM_DNSQ, po, pl);
     uint32_t name = CLK_N_NA;
-    if (type == NM_DNSQ) name = dns_query_verdict(T, pk + po, pl, mask);
-    else if (type == NM_DNSQ_TCP) {
+    if (kType == (int)NM_DNSQ) name = dns_query_verdict(T, pk + po, pl, mask);
+    else if (kType == (int)NM_DNSQ_TCP) {
         const bool framed = pl >= 2 && gbe16(pk + po) + 2 <= pl;
         const uint32_t v = dns_query_verdict(T, pk + (po + 2), framed ? gbe16(pk + po) : 0u, mask);
         if (pl > 0) name = framed ? v : CLK_N_DENY;
     }
-    else if (type == NM_HTTP) { if (pl > 0) name = http_host_verdict(T, pk + po, pl); }
+    else if (kType == (int)NM_HTTP) { if (pl > 0) name = http_host_verdict(T, pk + po, pl); }
     else { const uint32_t v = tls_sni_verdict(T, pk + po, pl, mask); if (pl > 0) name = v; }
     return word | (name << 4);
 }
 
-struct VcMeta { uint32_t pkoff, words, lists, cnt, total; };
-__host__ __device__ inline VcMeta vc_meta(uint32_t threads)
+template <int kType, int kMinB>
+__global__ void __launch_bounds__(256, kMinB) k_name_list(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts, uint4 *__restrict__ ents,
+                                                   uint32_t *__restrict__ cnt, uint32_t cap, uint32_t *__restrict__ verdicts)
 {
-    VcMeta M; uint32_t o = 0;
-    M.pkoff = o; o += threads * 4;                 // per packet: span offset (16 B units) | captured length (16 B units) << 16
-    M.words = o; o += threads * 4;                 // phase-A verdict word
-    M.lists = o; o += VC_LISTS * threads * 2;      // u16 thread indices per work type
-    M.cnt = o; o += 2 * 8 * 4;                     // list lengths, double-buffered by chunk parity
-    M.total = (o + 15u) & ~15u;
-    return M;
-}
-
-// rest_q: [0] entries appended, [1] overflow flag, [2..2+rest_cap) packet indices
-template <int kThreads, int kCap, int kMinBlocks>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) k_varlen_chunk(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts,
-                                                                      const uint32_t *__restrict__ offs16, uint32_t n, uint32_t flags,
-                                                                      uint32_t *__restrict__ verdicts, uint32_t *__restrict__ rest_q, uint32_t rest_cap)
-{
-    extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr uint32_t kWarps = kThreads / 32;
-    const VcMeta M = vc_meta(kThreads);
-    const SmemLayout L = smem_layout(T, 2 * kCap, M.total, 2, MSLOTS, kWarps);
-    Tabs tb; MetricAgg ag;
-    cta_prologue<false>(T, smem, L, 2, tb, ag);
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint64_t *bars = (uint64_t *)(smem + L.bars);
-    uint8_t *bufs = smem + L.tiles;
-    uint32_t *pkoff = (uint32_t *)(smem + L.queue + M.pkoff), *words = (uint32_t *)(smem + L.queue + M.words);
-    uint16_t *lists = (uint16_t *)(smem + L.queue + M.lists);
-    uint32_t *cnt = (uint32_t *)(smem + L.queue + M.cnt);
-    if (tid < 16) cnt[tid] = 0;
-    const uint32_t n_chunks = (n + kThreads - 1) / kThreads;
-    const bool do_metrics = !(flags & CLK_F_NO_METRICS);
-    __syncthreads();                                        // tables staged, aggregation table and counters zeroed, barriers initialised
-
-    // thread 0: start the bulk copy of chunk c into stage s (nothing is copied for an empty or oversize span)
-    auto issue = [&](uint32_t c, uint32_t s) {
-        if (c >= n_chunks) return;
-        const uint32_t lo = c * kThreads, hi = (n - lo < (uint32_t)kThreads) ? n : lo + kThreads;
-        const uint32_t o_lo = __ldg(&offs16[lo]), units = __ldg(&offs16[hi]) - o_lo;
-        if (units != 0 && units <= kCap / 16) {
-            mbar_expect_tx(&bars[s], units * 16);
-            tma_load_1d(bufs + s * kCap, pkts + (unsigned long long)o_lo * 16ull, units * 16, &bars[s]);
-        }
+    const uint32_t n_k = cnt[kType] < cap ? cnt[kType] : cap;
+    const uint32_t lane = threadIdx.x & 31u, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, W = (gridDim.x * blockDim.x) >> 5;
+    const uint4 *mine = ents + (size_t)kType * cap;
+    // The parsers walk their frame through chains of dependent byte loads; a frame's lines beyond the first 64 bytes have not
+    // been touched since the capture was written, so every new line would cost a DRAM round trip in the middle of a chain.
+    // Each lane therefore asks for ALL lines of its frame at once (L2 prefetch, no register cost) — for this unit right away
+    // and for the warp's next unit one unit ahead.
+    auto prefetch_frame = [&](const uint4 &en) {
+        const uint8_t *q = pkts + (unsigned long long)en.z * 16ull; const uint32_t bytes = en.w * 16u;
+        for (uint32_t o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
     };
-    if (tid == 0) { issue(blockIdx.x, 0); issue(blockIdx.x + gridDim.x, 1); }
-
-    uint32_t it = 0, uses0 = 0, uses1 = 0;                  // completed copies per stage (an unstaged chunk does not flip its barrier)
-    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x, it++) {
-        const uint32_t s = it & 1u;
-        const uint32_t lo = c * kThreads, hi = (n - lo < (uint32_t)kThreads) ? n : lo + kThreads, i = lo + tid;
-        const bool valid = i < hi;
-        const uint32_t o_lo = __ldg(&offs16[lo]), units = __ldg(&offs16[hi]) - o_lo;
-        const uint32_t o0 = valid ? __ldg(&offs16[i]) : 0u, o1 = valid ? __ldg(&offs16[i + 1]) : 0u;
-        const bool staged = units != 0 && units <= kCap / 16;
-        uint32_t *cur = cnt + s * 8;
-        if (staged) { mbar_wait(&bars[s], (s ? uses1 : uses0) & 1u); if (s) uses1++; else uses0++; }
-        const uint8_t *buf = bufs + s * kCap;
-
-        // ---- phase A -------------------------------------------------------------------------------------------------
-        bool hm = false; unsigned long long mk = 0; uint32_t w = 0, kind = 0;          // kind: 0 done, 1..5 name work, 6 rest
-        if (valid) {
-            const uint32_t avail = (o1 - o0) * 16u;
-            kind = 6;
-            if (staged && avail >= 64) {
-                const uint8_t *b = buf + (o0 - o_lo) * 16u;
-                const uint32_t w3 = *(const uint32_t *)(b + 12);
-                const uint4 q1 = *(const uint4 *)(b + 16);
-                const uint4 q2 = *(const uint4 *)(b + 32);
-                uint32_t nm;
-                if (fast_classify<true>(T, tb, w3, q1, q2.x, q2.y, q2.w, avail, flags, w, hm, mk, nm)) {
-                    kind = nm;
-                    if (nm == NM_TLS && T.n_http) {                                     // plaintext HTTP shares the egress port with TLS
-                        const uint32_t po = 34 + ((q2.w >> 20) & 0xfu) * 4;              // < end <= avail (fast_classify checked)
-                        if (b[po] != 0x16u) kind = NM_HTTP;
-                    }
-                    if (nm != NM_NONE) { pkoff[tid] = (o0 - o_lo) | ((o1 - o0) << 16); words[tid] = w; }
-                }
-            }
-            if (kind == 0) stg_stream(&verdicts[i], w);
-            else if (kind == 6) stg_stream(&verdicts[i], CLK_W_REST);
-        }
-        if (do_metrics) metric_warp_emit(T, ag, hm, mk);
-        #pragma unroll
-        for (uint32_t k = 1; k <= VC_LISTS; k++) {
-            const unsigned m = __ballot_sync(0xffffffffu, kind == k);
-            if (m) {
+    uint4 ent_n = make_uint4(0, 0, 0, 0);
+    if (gw * 32u + lane < n_k) { ent_n = mine[gw * 32u + lane]; prefetch_frame(ent_n); }
+    for (uint32_t u = gw; u * 32u < n_k; u += W) {
+        const uint32_t e = u * 32u + lane; const bool valid = e < n_k;
+        const uint4 ent = ent_n;
+        { const uint32_t en = (u + W) * 32u + lane; ent_n = make_uint4(0, 0, 0, 0); if (en < n_k) { ent_n = mine[en]; prefetch_frame(ent_n); } }
+        const uint8_t *pk = pkts + (unsigned long long)ent.z * 16ull; const uint32_t avail = ent.w * 16u;
+        bool defer = false;
+        if (kType == (int)NM_TLS && T.n_http) {                 // plaintext HTTP shares the egress port with TLS: those go to the HTTP list
+            if (valid) { uint32_t po, pl; payload_window(pk, avail, true, po, pl); defer = pl >= 1 && gb(pk + po) != 0x16u; }
+            const unsigned dm = __ballot_sync(0xffffffffu, defer);
+            if (dm) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&cur[k], (uint32_t)__popc(m));
+                if (lane == 0) base = atomicAdd(&cnt[NM_HTTP], (uint32_t)__popc(dm));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (kind == k) lists[(k - 1) * kThreads + base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)tid;
+                const uint32_t pos = base + __popc(dm & ((1u << lane) - 1u));
+                if (defer && pos < cap) ents[(size_t)NM_HTTP * cap + pos] = ent;
             }
         }
-        {
-            const unsigned m = __ballot_sync(0xffffffffu, kind == 6);
-            if (m) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&rest_q[0], (uint32_t)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (kind == 6) {
-                    const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (pos < rest_cap) rest_q[2 + pos] = i; else rest_q[1] = 1u;
-                }
-            }
-        }
-        __syncthreads();                                    // lists complete
-        if (tid < 8) cnt[(s ^ 1u) * 8 + tid] = 0;            // the other parity's counters: last read before the previous chunk's final barrier
-
-        // ---- phase B: 32-entry units of the lists, shared out over the warps ----------------------------------------
-        {
-            uint32_t u = 0;
-            #pragma unroll 1
-            for (uint32_t k = 1; k <= VC_LISTS; k++) {
-                const uint32_t len = cur[k];
-                #pragma unroll 1
-                for (uint32_t e0 = 0; e0 < len; e0 += 32, u++) {
-                    if (u % kWarps != warp) continue;
-                    const uint32_t e = e0 + lane;
-                    const unsigned um = __ballot_sync(0xffffffffu, e < len);          // the unit's lanes (the loop is warp-uniform)
-                    if (e < len) {
-                        const uint32_t t = lists[(k - 1) * kThreads + e], po = pkoff[t];
-                        const SP pk = SP{ smem_u32(buf) + (po & 0xffffu) * 16u };
-                        stg_stream(&verdicts[lo + t], name_work(T, pk, (po >> 16) * 16u, k, words[t], um));
-                    }
-                }
-            }
-        }
-        __syncthreads();                                    // every reader of this stage is done
-        if (tid == 0) { fence_proxy_async(); issue(c + 2 * gridDim.x, s); }
+        const bool run = valid && !defer;
+        const unsigned um = __ballot_sync(0xffffffffu, run);
+        if (run) stg_stream(&verdicts[ent.x], name_work_t<kType>(T, pk, avail, ent.y, um));
     }
-    if (do_metrics) metric_cta_flush(T, ag);
 }
 
-// The packets k_varlen_chunk left behind (CLK_W_REST): the generic path, straight from global memory.
-__global__ void __launch_bounds__(256) k_varlen_rest(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts,
-                                                     const uint32_t *__restrict__ offs16, uint32_t n, uint32_t flags,
-                                                     uint32_t *__restrict__ verdicts, const uint32_t *__restrict__ rest_q, uint32_t rest_cap)
+// List 0: the frames the fast ladder does not cover — the generic path (its metrics included).
+__global__ void __launch_bounds__(256) k_generic_list(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts, const uint4 *__restrict__ ents,
+                                                      const uint32_t *__restrict__ cnt, uint32_t cap, uint32_t flags, uint32_t *__restrict__ verdicts)
 {
-    const uint32_t cnt = rest_q[0], overflow = rest_q[1];
-    if (cnt == 0) return;
+    const uint32_t n_k = cnt[0] < cap ? cnt[0] : cap;
+    if (n_k == 0) return;
     extern __shared__ __align__(1024) uint8_t smem[];
     const SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
     Tabs tb; MetricAgg ag;
     cta_prologue<false>(T, smem, L, 0, tb, ag);
     __syncthreads();
     const bool do_metrics = !(flags & CLK_F_NO_METRICS);
-    const uint32_t step = gridDim.x * blockDim.x, g = blockIdx.x * blockDim.x + threadIdx.x;
-    // queue overflow (more leftovers than the queue holds): find them by their mark instead
-    const uint32_t total = overflow ? n : (cnt < rest_cap ? cnt : rest_cap), total_round = (total + 31u) & ~31u;
-    for (uint32_t k = g; k < total_round; k += step) {
+    const uint32_t step = gridDim.x * blockDim.x, n_round = (n_k + 31u) & ~31u;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += step) {
         bool hm = false; unsigned long long mk = 0;
-        if (k < total) {
-            const uint32_t j = overflow ? k : rest_q[2 + k];
-            if (!overflow || verdicts[j] == CLK_W_REST) {
-                const uint32_t o0 = __ldg(&offs16[j]), o1 = __ldg(&offs16[j + 1]);
-                stg_stream(&verdicts[j], generic_one(T, tb, pkts + (unsigned long long)o0 * 16ull, (o1 - o0) * 16u, flags, hm, mk));
-            }
+        if (k < n_k) {
+            const uint4 ent = ents[k];
+            stg_stream(&verdicts[ent.x], generic_one(T, tb, pkts + (unsigned long long)ent.z * 16ull, ent.w * 16u, flags, hm, mk));
         }
         if (do_metrics) metric_warp_emit(T, ag, hm, mk);
     }
@@ -1381,46 +1367,87 @@ const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride
 #undef FAST_ARGS
 }
 
-template <int kThreads, int kCap, int kMinBlocks>
-static const char *launch_chunk(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, uint32_t n, uint32_t flags,
-                                uint32_t *d_verdicts, cudaStream_t st, uint32_t *rest_q, uint32_t rest_cap, LaunchInfo *info)
+static uint32_t varlen_slice() { uint32_t v = 8u << 20; if (const char *s = getenv("CLK_SLICE")) { long x = atol(s); if (x >= 1024) v = (uint32_t)x; } return v; }
+
+template <int kType>
+static cudaError_t launch_name_list(const DevTables &T, const void *d_pkts, uint4 *ents, uint32_t *cnt, uint32_t cap, uint32_t *d_verdicts, int sms, cudaStream_t st)
 {
-    int grid = 0; cudaError_t e;
-    const SmemLayout L = smem_layout(T, 2 * kCap, vc_meta(kThreads).total, 2, MSLOTS, kThreads / 32);
-    if ((e = occupancy_grid(T, k_varlen_chunk<kThreads, kCap, kMinBlocks>, kThreads, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);
-    const uint32_t need = (n + kThreads - 1) / kThreads; if ((uint32_t)grid > need) grid = (int)need;
-    if ((e = cudaMemsetAsync(rest_q, 0, 8, st)) != cudaSuccess) return cudaGetErrorString(e);
-    k_varlen_chunk<kThreads, kCap, kMinBlocks><<<grid, kThreads, L.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, n, flags, d_verdicts, rest_q, rest_cap);
-    if (info) { info->grid = grid; info->block = kThreads; info->smem = L.total; info->launches = 2; }
-    if ((e = cudaGetLastError()) != cudaSuccess) return cudaGetErrorString(e);
-    const SmemLayout R = smem_layout(T, 0, 0, 0, MSLOTS, 8);
-    int rgrid = 0;
-    if ((e = occupancy_grid(T, k_varlen_rest, 256, R.total, &rgrid)) != cudaSuccess) return cudaGetErrorString(e);
-    if ((uint32_t)rgrid > (n + 255) / 256) rgrid = (int)((n + 255) / 256);
-    k_varlen_rest<<<rgrid, 256, R.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, n, flags, d_verdicts, rest_q, rest_cap);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+    static int nb = 0;                                                          // CTAs of 256 threads per SM (registers per thread follow): tuning knob CLK_NB
+    if (!nb) { nb = 3; if (const char *s = getenv("CLK_NB")) { int v = atoi(s); if (v >= 2 && v <= 4) nb = v; } }
+    const int grid = sms * nb;
+    if (nb == 2) k_name_list<kType, 2><<<grid, 256, 0, st>>>(T, (const uint8_t *)d_pkts, ents, cnt, cap, d_verdicts);
+    else if (nb == 4) k_name_list<kType, 4><<<grid, 256, 0, st>>>(T, (const uint8_t *)d_pkts, ents, cnt, cap, d_verdicts);
+    else k_name_list<kType, 3><<<grid, 256, 0, st>>>(T, (const uint8_t *)d_pkts, ents, cnt, cap, d_verdicts);
+    return cudaGetLastError();
 }
 
-uint32_t varlen_rest_cap(unsigned long long n) { return (uint32_t)(n / 8 + 65536); }
+// Work lists of one slice: 8 counters (padded to 256 bytes) + VW_LISTS lists of `cap` 16-byte entries; two such sets (slice
+// parity), so the head kernel of slice j + 1 fills one while the parser kernels of slice j read the other.
+static size_t varlen_set_bytes(uint32_t cap) { return 256 + (size_t)VW_LISTS * cap * 16; }
+size_t varlen_scratch_bytes(unsigned long long n) { const uint32_t cap = (uint32_t)(n < varlen_slice() ? n : varlen_slice()); return 2 * varlen_set_bytes(cap) + 256; }
 
-// rest_q: device scratch of (2 + varlen_rest_cap(n)) words owned by this launch (the engine keeps one per stream)
+#define CU_TRY(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cudaGetErrorString(_e); } while (0)
+
+// The batch in slices; per slice: head kernel + generic list on `st`, then the parser kernels on three side streams (each
+// runs one or two parsers; they are latency-bound and share the SMs with each other and with the NEXT slice's head kernel,
+// which is why the head kernel is launched with one CTA per SM).  `st` joins every side stream before returning.
+template <int kWarps, int kMinBlocks, int kPerSM>
+static const char *launch_pipeline(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n, uint32_t flags,
+                                   uint32_t *d_verdicts, cudaStream_t st, const VarlenCtx *ctx, LaunchInfo *info)
+{
+    const uint32_t cap = (uint32_t)(n < varlen_slice() ? n : varlen_slice());
+    if (!ctx || !ctx->scratch || ctx->scratch_bytes < 2 * varlen_set_bytes(cap)) return "varlen scratch too small";
+    const int sms = sm_count() - reserved_sms(T);
+    const SmemLayout L = smem_layout(T, 0, kWarps * VW_LISTS * VW_QCAP * 16, 0, MSLOTS, kWarps);
+    CU_TRY(cudaFuncSetAttribute(k_varlen_head<kWarps, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    const SmemLayout G = smem_layout(T, 0, 0, 0, MSLOTS, 8);
+    CU_TRY(cudaFuncSetAttribute(k_generic_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total));
+    const bool names = (flags & CLK_F_NAME_STAGE) != 0;
+    uint32_t launches = 0, slice = 0;
+    for (unsigned long long first = 0; first < n; first += cap, slice++) {
+        const uint32_t ns = (uint32_t)(n - first < cap ? n - first : cap), p = slice & 1u;
+        uint32_t *cnt = (uint32_t *)((uint8_t *)ctx->scratch + p * varlen_set_bytes(cap)); uint4 *ents = (uint4 *)((uint8_t *)cnt + 256);
+        if (names && slice >= 2) for (int a = 0; a < 3; a++) CU_TRY(cudaStreamWaitEvent(st, ctx->ev_done[p][a], 0));     // the parsers of slice - 2 have left this set
+        CU_TRY(cudaMemsetAsync(cnt, 0, 32, st));
+        unsigned long long need = ((unsigned long long)(ns + 31) / 32 + kWarps - 1) / kWarps; const int g1 = (unsigned long long)(sms * kPerSM) > need ? (int)need : sms * kPerSM;
+        k_varlen_head<kWarps, kMinBlocks><<<g1, kWarps * 32, L.total, st>>>(T, (const uint8_t *)d_pkts, d_offs16, (uint32_t)first, ns, flags, d_verdicts, ents, cnt, cap);
+        CU_TRY(cudaGetLastError());
+        if (info) { info->grid = g1; info->block = kWarps * 32; info->smem = L.total; }
+        k_generic_list<<<sms, 256, G.total, st>>>(T, (const uint8_t *)d_pkts, ents, cnt, cap, flags, d_verdicts);
+        CU_TRY(cudaGetLastError());
+        launches += 2;
+        if (!names) continue;
+        CU_TRY(cudaEventRecord(ctx->ev_head[p], st));
+        for (int a = 0; a < 3; a++) CU_TRY(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_head[p], 0));
+        CU_TRY(launch_name_list<(int)NM_DNSQ>(T, d_pkts, ents, cnt, cap, d_verdicts, sms, ctx->aux[0]));
+        CU_TRY(launch_name_list<(int)NM_DNSQ_TCP>(T, d_pkts, ents, cnt, cap, d_verdicts, sms, ctx->aux[0]));
+        CU_TRY(launch_name_list<(int)NM_TLS>(T, d_pkts, ents, cnt, cap, d_verdicts, sms, ctx->aux[1]));
+        if (T.n_http) { CU_TRY(launch_name_list<(int)NM_HTTP>(T, d_pkts, ents, cnt, cap, d_verdicts, sms, ctx->aux[1])); launches++; }
+        CU_TRY(launch_name_list<(int)NM_DNSA>(T, d_pkts, ents, cnt, cap, d_verdicts, sms, ctx->aux[2]));
+        launches += 4;
+        for (int a = 0; a < 3; a++) CU_TRY(cudaEventRecord(ctx->ev_done[p][a], ctx->aux[a]));
+    }
+    if (names) {                                                                // join: the caller's stream sees everything done
+        const uint32_t last = slice ? slice - 1 : 0;
+        for (uint32_t q = 0; q < 2 && q <= last; q++) for (int a = 0; a < 3; a++) CU_TRY(cudaStreamWaitEvent(st, ctx->ev_done[(last - q) & 1u][a], 0));
+    }
+    if (info) info->launches = launches;
+    return nullptr;
+}
+
 const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n, uint32_t flags,
-                          uint32_t *d_verdicts, cudaStream_t st, uint32_t *rest_q, LaunchInfo *info)
+                          uint32_t *d_verdicts, cudaStream_t st, const VarlenCtx *ctx, LaunchInfo *info)
 {
     if (n == 0) return nullptr;
     int grid = 0; cudaError_t e;
-    if (n < 0x7fffffffull && rest_q && !getenv("CLK_VARLEN_GENERIC")) {
-        const uint32_t cap = varlen_rest_cap(n);
-        int cfg = 0; if (const char *s = getenv("CLK_VC")) cfg = atoi(s);
-#define VC_ARGS T, d_pkts, d_offs16, (uint32_t)n, flags, d_verdicts, st, rest_q, cap, info
-        switch (cfg) {
-        case 1:  return launch_chunk<256, 36 * 1024, 2>(VC_ARGS);
-        case 2:  return launch_chunk<128, 20 * 1024, 4>(VC_ARGS);
-        case 3:  return launch_chunk<512, 72 * 1024, 1>(VC_ARGS);
-        default: return launch_chunk<192, 28 * 1024, 3>(VC_ARGS);
+    if (n < 0xfffffff0ull && !getenv("CLK_VARLEN_GENERIC")) {
+        int cfgw = 0; if (const char *sw = getenv("CLK_VW")) cfgw = atoi(sw);
+        switch (cfgw) {
+        case 1:  return launch_pipeline<16, 2, 1>(T, d_pkts, d_offs16, n, flags, d_verdicts, st, ctx, info);   // 64 registers, one CTA per SM: leaves half an SM to the parsers
+        case 2:  return launch_pipeline<8, 4, 2>(T, d_pkts, d_offs16, n, flags, d_verdicts, st, ctx, info);
+        case 3:  return launch_pipeline<8, 4, 3>(T, d_pkts, d_offs16, n, flags, d_verdicts, st, ctx, info);
+        default: return launch_pipeline<16, 2, 2>(T, d_pkts, d_offs16, n, flags, d_verdicts, st, ctx, info);
         }
-#undef VC_ARGS
     }
     SmemLayout L = smem_layout(T, 0, 0, 0, MSLOTS, 8);
     if ((e = occupancy_grid(T, k_generic<true>, 256, L.total, &grid)) != cudaSuccess) return cudaGetErrorString(e);

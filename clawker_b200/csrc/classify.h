@@ -13,10 +13,17 @@ struct LaunchInfo { uint32_t grid, block, smem, launches; };   // launches: kern
 // All launchers enqueue on `st` and return nullptr on success or a static error string.
 const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride, unsigned long long n, uint32_t flags,
                          uint32_t *d_verdicts, cudaStream_t st, int loader, int stages, uint32_t *rare_q, uint32_t *rare_cnt, LaunchInfo *info);
-// rest_q: device scratch of (2 + varlen_rest_cap(n)) u32 owned by this launch until it completes (leftover-frame queue)
-uint32_t varlen_rest_cap(unsigned long long n);
+// Per caller stream: the work lists of the varlen kernel pipeline (varlen_scratch_bytes(n) bytes of device memory) and the
+// side streams / events it forks onto.  Owned by the engine; a launch uses it until everything it enqueued has completed.
+struct VarlenCtx {
+    void *scratch = nullptr; size_t scratch_bytes = 0;
+    cudaStream_t aux[3] = { nullptr, nullptr, nullptr };
+    cudaEvent_t ev_head[2] = { nullptr, nullptr };
+    cudaEvent_t ev_done[2][3] = { { nullptr, nullptr, nullptr }, { nullptr, nullptr, nullptr } };
+};
+size_t varlen_scratch_bytes(unsigned long long n);
 const char *launch_varlen(const DevTables &T, const void *d_pkts, const uint32_t *d_offs16, unsigned long long n, uint32_t flags,
-                          uint32_t *d_verdicts, cudaStream_t st, uint32_t *rest_q, LaunchInfo *info);
+                          uint32_t *d_verdicts, cudaStream_t st, const VarlenCtx *ctx, LaunchInfo *info);
 const char *launch_hdr16(const DevTables &T, const void *d_recs, const void *d_aux, unsigned long long n, uint32_t flags, uint32_t *d_verdicts,
                          cudaStream_t st, LaunchInfo *info);
 const char *launch_events(const DevTables &T, const clk_event *d_ev, unsigned long long n, uint32_t flags, uint32_t *d_verdicts,

@@ -89,7 +89,7 @@ static_assert(sizeof(Ep6Key) == 32, "Ep6Key");
 struct NameSlot {
     uint64_t key;               // name_key(hash, len)
     uint32_t val;               // zones: DomainHash(zone) (types.go:121-125); SNI: entry index
-    uint32_t str_off;           // offset into names blob: [len u8][bytes]
+    uint32_t str_off;           // length << 24 | (offset into the names blob) / 16: lower-case bytes, 16-byte aligned, zero padded
 };
 
 enum { HTTP_K_EXACT = 0, HTTP_K_SUFFIX = 1, HTTP_K_PREFIX = 2 };

@@ -100,6 +100,8 @@ struct clk_engine {
     DevBuf work_rare[3];                       // rare / leftover-frame queues of the host pipeline lanes
     std::map<cudaStream_t, DevBuf> scratch;    // the same for the *_dev entries: one per caller stream, so launches in flight on
                                                // different streams of one engine never share a queue
+    struct VarlenState { DevBuf buf; VarlenCtx ctx; };
+    std::map<cudaStream_t, VarlenState> varlen; // work lists + side streams / events of the varlen kernel pipeline, per caller stream
     DevBuf work_pkts[3], work_offs[3], work_verd[3], scan_sums, scan_pos, scan_total, upd_out, ctr_block;
     // multi-GPU (clk_comm_*): one NCCL communicator per engine, engine-owned gather buffers
     ncclComm_t comm = nullptr; int comm_rank = 0, comm_world = 1;
@@ -199,13 +201,14 @@ void build_name_table(const std::vector<std::string> &names, const std::vector<u
     for (size_t i = 0; i < names.size(); i++) {
         const std::string &s = names[i];
         if (s.size() > 255) continue;
-        uint32_t off = (uint32_t)blob.size();
-        blob.push_back((uint8_t)s.size());
+        while (blob.size() % 16) blob.push_back(0);                        // entries are 16-byte aligned and zero padded (name_load64)
+        const uint32_t off16 = (uint32_t)(blob.size() / 16);
         for (unsigned char c : s) blob.push_back((c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c);
+        while (blob.size() % 16) blob.push_back(0);
         uint64_t key = name_key_of(s);
         uint32_t h = name_home(key, cap - 1);
         while (slots[h].key) h = (h + 1) & (cap - 1);
-        slots[h] = NameSlot{ key, vals[i], off };
+        slots[h] = NameSlot{ key, vals[i], ((uint32_t)s.size() << 24) | off16 };
     }
 }
 
@@ -451,6 +454,7 @@ int publish_locked(clk_engine *e)
         }
         build_name_table(names, vals, http_slots, blob);
     }
+    if (blob.size() >= (1ull << 28)) return fail(e, CLK_E2BIG, "name tables need %zu bytes of strings (limit 256 MiB)", blob.size());
     // ---- upload -------------------------------------------------------------------------------------
     CUDA_TRY(e, upload(S.crows, crows, st));       CUDA_TRY(e, upload(S.cg_slots, cg_slots, st));
     // the fields the fast path needs, packed as three 16-byte words per row (48 B stride: conflict-free LDS.128 for 8 rows)
@@ -530,6 +534,23 @@ int publish_locked(clk_engine *e)
         ctr[1] = reimport.size();                        // the key counter the max_entries gate reads
         CUDA_TRY(e, cudaMemcpy(e->m_dropped.p, ctr, 16, cudaMemcpyHostToDevice));
     }
+    return CLK_OK;
+}
+
+// Work lists, side streams and events of the varlen pipeline for launches enqueued on `st` (created on first use).
+int varlen_ctx(clk_engine *e, cudaStream_t st, uint64_t n, const VarlenCtx **out)
+{
+    clk_engine::VarlenState &v = e->varlen[st];
+    if (!v.ctx.aux[0]) {
+        for (int a = 0; a < 3; a++) CUDA_TRY(e, cudaStreamCreateWithFlags(&v.ctx.aux[a], cudaStreamNonBlocking));
+        for (int p = 0; p < 2; p++) {
+            CUDA_TRY(e, cudaEventCreateWithFlags(&v.ctx.ev_head[p], cudaEventDisableTiming));
+            for (int a = 0; a < 3; a++) CUDA_TRY(e, cudaEventCreateWithFlags(&v.ctx.ev_done[p][a], cudaEventDisableTiming));
+        }
+    }
+    CUDA_TRY(e, v.buf.ensure(varlen_scratch_bytes(n)));
+    v.ctx.scratch = v.buf.p; v.ctx.scratch_bytes = v.buf.cap;
+    *out = &v.ctx;
     return CLK_OK;
 }
 
@@ -622,6 +643,11 @@ try {
         for (DevBuf *b : { &e->m_keys, &e->m_counts, &e->m_dropped, &e->g_keys, &e->g_counts, &e->g_dropped, &e->scan_sums, &e->scan_pos, &e->scan_total, &e->upd_out, &e->ctr_block }) b->release();
         for (int i = 0; i < 3; i++) e->work_rare[i].release();
         for (auto &kv : e->scratch) kv.second.release();
+        for (auto &kv : e->varlen) {
+            kv.second.buf.release();
+            for (int a = 0; a < 3; a++) if (kv.second.ctx.aux[a]) cudaStreamDestroy(kv.second.ctx.aux[a]);
+            for (int p = 0; p < 2; p++) { if (kv.second.ctx.ev_head[p]) cudaEventDestroy(kv.second.ctx.ev_head[p]); for (int a = 0; a < 3; a++) if (kv.second.ctx.ev_done[p][a]) cudaEventDestroy(kv.second.ctx.ev_done[p][a]); }
+        }
         comm_release(e);
         for (int i = 0; i < 3; i++) { e->work_pkts[i].release(); e->work_offs[i].release(); e->work_verd[i].release(); if (e->pipe[i]) cudaStreamDestroy(e->pipe[i]); }
         if (e->ev0) cudaEventDestroy(e->ev0);
@@ -866,9 +892,9 @@ try {
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     LaunchInfo li = { 0, 0, 0, 0 };
     if (!stream) cudaEventRecord(e->ev0, st);                 // a caller that brings its own stream brings its own events
-    DevBuf &sc = e->scratch[st];
-    CUDA_TRY(e, sc.ensure(((size_t)varlen_rest_cap(n) + 2) * 4));
-    const char *err = launch_varlen(e->T, d_pkts, (const uint32_t *)d_offs16, n, flags, (uint32_t *)d_verdicts, st, (uint32_t *)sc.p, &li);
+    const VarlenCtx *vc = nullptr;
+    rc = varlen_ctx(e, st, n, &vc); if (rc) return rc;
+    const char *err = launch_varlen(e->T, d_pkts, (const uint32_t *)d_offs16, n, flags, (uint32_t *)d_verdicts, st, vc, &li);
     if (!stream) cudaEventRecord(e->ev1, st);
     return finish_launch(e, err, li);
 } CLK_GUARD_INT(e)
@@ -903,9 +929,9 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
             CUDA_TRY(e, cudaMemcpyAsync(e->work_offs[s].p, offs16 + done, (cnt + 1) * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + b0, b1 - b0, cudaMemcpyHostToDevice, st));
             // offsets stay absolute: bias the base pointer instead of rewriting them
-            CUDA_TRY(e, e->work_rare[s].ensure(((size_t)varlen_rest_cap(cnt) + 2) * 4));
-            err = launch_varlen(e->T, (const uint8_t *)e->work_pkts[s].p - b0, (const uint32_t *)e->work_offs[s].p, cnt, flags, (uint32_t *)e->work_verd[s].p, st,
-                                (uint32_t *)e->work_rare[s].p, &li);
+            const VarlenCtx *vc = nullptr;
+            rc = varlen_ctx(e, st, cnt, &vc); if (rc) return rc;
+            err = launch_varlen(e->T, (const uint8_t *)e->work_pkts[s].p - b0, (const uint32_t *)e->work_offs[s].p, cnt, flags, (uint32_t *)e->work_verd[s].p, st, vc, &li);
         } else {
             CUDA_TRY(e, e->work_pkts[s].ensure(cnt * stride));
             CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + done * stride, cnt * stride, cudaMemcpyHostToDevice, st));

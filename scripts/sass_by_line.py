@@ -26,7 +26,7 @@ for (c, _), (n, a, s) in zip(insts, prof):
 tot = sum(v[0] for v in agg.values()); tots = sum(v[2] for v in agg.values())
 src = {}
 d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "clawker_b200", "csrc")
-for f in os.listdir(d):
+for f in [x for x in os.listdir(d) if os.path.isfile(os.path.join(d, x))]:
     src[f] = open(os.path.join(d, f)).read().split("\n")
 print(f"total warp-inst {tot}, samples {tots}")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:

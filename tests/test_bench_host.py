@@ -143,6 +143,7 @@ class _FakeEngine:
     def close(self): pass
 
     def classify_slots(self, pk, stride, flags, out=None): pass
+    def classify_hdr16(self, recs, aux, flags, out=None): pass
     def classify_varlen(self, pk, offs, flags, out=None): pass
 
     def totals_merge(self, ptr, world):
@@ -167,6 +168,7 @@ def _dry_run(monkeypatch, capsys, world, workload):
     import torch
     import torch.distributed as dist
     from clawker_b200 import engine
+    from clawker_b200 import abi as abi_mod
     cpu = torch.device("cpu")
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
     monkeypatch.setattr(torch.cuda, "set_device", lambda i: None)
@@ -179,6 +181,7 @@ def _dry_run(monkeypatch, capsys, world, workload):
     for name in ("init_process_group", "barrier", "destroy_process_group", "all_gather_into_tensor", "all_reduce", "broadcast_object_list"):
         monkeypatch.setattr(dist, name, lambda *a, **k: None)
     monkeypatch.setattr(engine, "comm_unique_id", lambda: b"\0" * 128)
+    monkeypatch.setattr(engine, "pack_hdr16", lambda pk, stride=64, pinned=False: (np.zeros(pk.size // stride, dtype=abi_mod.HDR16_DTYPE), np.zeros(0, np.uint8)))
     monkeypatch.setattr(engine, "Engine", _FakeEngine)
     monkeypatch.setattr(engine, "pinned_empty", lambda n: np.empty(n, dtype=np.uint8))
     monkeypatch.setitem(bench.WORKLOADS[workload], "gen", 4096)
@@ -199,10 +202,11 @@ def test_run_gpu_flow_single(monkeypatch, capsys):
     assert d["n_gpus"] == 1 and d["gpu_launches"] == 4 and d["config"]["parallelism"] == "single GPU"
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["clocks"]["reasons"] == ["unavailable"]
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] == 8192 * 64
+    assert d["e2e_compact"]["h2d_bytes_per_step"] == 8192 * 16 and d["e2e_compact"]["bytes_per_packet_over_pcie"] == 20.0
 
 
 def test_run_gpu_flow_multi_and_varlen(monkeypatch, capsys):
     d = _dry_run(monkeypatch, capsys, 2, "c2")
     assert d["n_gpus"] == 2 and d["gpu_launches"] == 8 and "4 SMs reserved" in d["config"]["collective"]     # classify + totals per step
     d = _dry_run(monkeypatch, capsys, 1, "c3h")
-    assert d["roofline"]["kernel"].startswith("clk::k_varlen") and d["config"]["layout"].startswith("varlen")
+    assert "k_varlen_head" in d["roofline"]["kernel"] and "e2e_compact" not in d and d["config"]["layout"].startswith("varlen")
