@@ -221,11 +221,26 @@ def _oracle_for(w, name_stage: bool, want_cidr: bool):
     return o, ("reference" if use_ref else "port")
 
 
-def host_threads() -> int:
+def cpu_quota() -> float | None:
+    """CPUs the container may use per the cgroup v2 quota (cpu.max "quota period"), None when unlimited / unknown."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        q, per = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        return None if q == "max" else float(q) / float(per)
     except Exception:
-        return os.cpu_count() or 1
+        return None
+
+
+def host_threads() -> int:
+    """Threads the CPU arm runs: one per CPU of the affinity mask, but no more than the cgroup CPU quota allows — threads
+    beyond the quota are only throttled (the GPU boxes show 128 CPUs under a 16-CPU quota)."""
+    try:
+        n = max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        n = os.cpu_count() or 1
+    q = cpu_quota()
+    if q is not None:
+        n = max(1, min(n, int(q + 0.5)))
+    return n
 
 
 def cpu_baseline(w, batch, samples: int = 5, warmup: int = 1, name_stage: bool = False, target_s: float = 2.0) -> dict:
@@ -256,6 +271,7 @@ def cpu_baseline(w, batch, samples: int = 5, warmup: int = 1, name_stage: bool =
               f"thread-private copies of the input, per-thread metrics maps (PERCPU, not merged), thread start-up excluded; median of {len(dts)} samples"
               + ("; IP/CIDR extension rules are not evaluated by the reference (SURVEY R4)" if kind == "reference" else ""))
     return {"value": round(per / med / 1e6, 2), "unit": "Mpackets/s", "cores": cores, "kind": kind, "sample": sample,
+            "cpus_visible": os.cpu_count(), "cpu_quota": cpu_quota(),
             "min": round(per / dts[-1] / 1e6, 2), "max": round(per / dts[0] / 1e6, 2), "samples": len(dts),
             "ms_per_step": round(med * 1e3, 3), "packets_per_step": per}
 
