@@ -880,15 +880,13 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) k_varlen_head(const _
     for (int k = 0; k < VW_LISTS; k++) qn[k] = 0;
 
     // the whole queue k of this warp -> global list k: one atomic, one coalesced store of 16-byte entries
-    auto flush = [&](int k) {
-        const uint32_t take = qn[k];
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&cnt[k], take);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < take && base + lane < cap) ents[(size_t)k * cap + base + lane] = queue[k * VW_QCAP + lane];
-        qn[k] = 0;
-        __syncwarp();
-    };
+    // (a macro, not a lambda taking k: the queue lengths must stay in registers)
+#define VW_FLUSH(k) do { \
+        const uint32_t take_ = qn[k]; uint32_t base_ = 0; \
+        if (lane == 0) base_ = atomicAdd(&cnt[k], take_); \
+        base_ = __shfl_sync(0xffffffffu, base_, 0); \
+        if (lane < take_ && base_ + lane < cap) ents[(size_t)(k) * cap + base_ + lane] = queue[(k) * VW_QCAP + lane]; \
+        qn[k] = 0; __syncwarp(); } while (0)
 
     // Software pipeline, two tiles deep: while tile t is classified, the header words of tile t + W and the offsets of
     // tile t + 2W are in flight (a warp keeps ~3 KB of loads outstanding; 16 warps cover the DRAM latency of an SM).
@@ -919,26 +917,29 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) k_varlen_head(const _
                 uint32_t nm;
                 if (fast_classify<true>(T, tb, w3, q1, q2.x, q2.y, q2.w, avail, flags, w, hm, mk, nm)) kind = nm == NM_NONE ? 0xffu : nm;
             }
+            if (kind == NM_DNSQ_TCP) { kind = 0; hm = false; }   // DNS over TCP is rare: the generic path redoes the packet (verdict, metric and name),
+                                                               // one list and one launch fewer — so nothing is counted for it here
             if (kind == 0xffu) stg_stream(&verdicts[first + i], w);
         }
         if (do_metrics) metric_warp_emit(T, ag, hm, mk);
         #pragma unroll
         for (int k = 0; k < VW_LISTS; k++) {
-            if (k == (int)NM_HTTP) continue;                   // filled by the ClientHello kernel, not here
+            if (k == (int)NM_HTTP || k == (int)NM_DNSQ_TCP) continue;           // HTTP is filled by the ClientHello kernel, not here
             const unsigned m = __ballot_sync(0xffffffffu, kind == (uint32_t)k);
             if (m) {
                 const uint32_t c = __popc(m);
-                if (qn[k] + c > VW_QCAP) flush(k);
+                if (qn[k] + c > VW_QCAP) VW_FLUSH(k);
                 if (kind == (uint32_t)k) queue[k * VW_QCAP + qn[k] + __popc(m & ((1u << lane) - 1u))] = make_uint4(first + i, w, o0, o1 - o0);
                 qn[k] += c;
                 __syncwarp();
-                if (qn[k] == VW_QCAP) flush(k);
+                if (qn[k] == VW_QCAP) VW_FLUSH(k);
             }
         }
         o0 = o0n; o1 = o1n; w3 = w3n; q1 = q1n; q2 = q2n; o0n = o0f; o1n = o1f;
     }
     #pragma unroll
-    for (int k = 0; k < VW_LISTS; k++) if (qn[k]) flush(k);
+    for (int k = 0; k < VW_LISTS; k++) if (qn[k]) VW_FLUSH(k);
+#undef VW_FLUSH
     if (do_metrics) metric_cta_flush(T, ag);
 }
 
@@ -1374,7 +1375,7 @@ const char *launch_slots(const DevTables &T, const void *d_pkts, uint32_t stride
 #undef FAST_ARGS
 }
 
-static uint32_t varlen_slice() { uint32_t v = 8u << 20; if (const char *s = getenv("CLK_SLICE")) { long x = atol(s); if (x >= 1024) v = (uint32_t)x; } return v; }
+static uint32_t varlen_slice() { uint32_t v = 12u << 20; if (const char *s = getenv("CLK_SLICE")) { long x = atol(s); if (x >= 1024) v = (uint32_t)x; } return v; }
 
 template <int kType>
 static cudaError_t launch_name_list(const DevTables &T, const void *d_pkts, uint4 *ents, uint32_t *cnt, uint32_t cap, uint32_t *d_verdicts, int sms, cudaStream_t st)
@@ -1427,11 +1428,10 @@ static const char *launch_pipeline(const DevTables &T, const void *d_pkts, const
         CU_TRY(cudaEventRecord(ctx->ev_head[p], st));
         for (int a = 0; a < 3; a++) CU_TRY(cudaStreamWaitEvent(ctx->aux[a], ctx->ev_head[p], 0));
         CU_TRY(launch_name_list<(int)NM_DNSQ>(T, d_pkts, ents, cnt, cap, d_verdicts, sms, ctx->aux[0]));
-        CU_TRY(launch_name_list<(int)NM_DNSQ_TCP>(T, d_pkts, ents, cnt, cap, d_verdicts, sms, ctx->aux[0]));
         CU_TRY(launch_name_list<(int)NM_TLS>(T, d_pkts, ents, cnt, cap, d_verdicts, sms, ctx->aux[1]));
         if (T.n_http) { CU_TRY(launch_name_list<(int)NM_HTTP>(T, d_pkts, ents, cnt, cap, d_verdicts, sms, ctx->aux[1])); launches++; }
         CU_TRY(launch_name_list<(int)NM_DNSA>(T, d_pkts, ents, cnt, cap, d_verdicts, sms, ctx->aux[2]));
-        launches += 4;
+        launches += 3;
         for (int a = 0; a < 3; a++) CU_TRY(cudaEventRecord(ctx->ev_done[p][a], ctx->aux[a]));
     }
     if (names) {                                                                // join: the caller's stream sees everything done
