@@ -886,6 +886,7 @@ try {
 int clk_classify_varlen_dev(clk_engine *e, const void *d_pkts, const void *d_offs16, uint64_t n, uint32_t flags, void *d_verdicts, void *stream)
 try {
     if (!e || (n && (!d_pkts || !d_verdicts || !d_offs16))) return fail(e, CLK_EINVAL, "NULL buffer");
+    if (((uintptr_t)d_pkts & 15u) || ((uintptr_t)d_offs16 & 3u) || ((uintptr_t)d_verdicts & 3u)) return fail(e, CLK_EINVAL, "d_pkts must be 16-byte aligned (frames are read with 16-byte loads), offs16 / verdicts 4-byte aligned");
     NEED_GPU(e);
     std::lock_guard<std::mutex> g(e->mu);
     int rc = ensure_published(e); if (rc) return rc;

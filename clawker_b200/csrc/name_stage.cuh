@@ -212,11 +212,12 @@ __device__ __noinline__ int dns_zone_select(const DevTables &T, P m, uint32_t ml
     bool stop = false;
     for (uint32_t i = end; i > off && nlab < want && !stop;) {   // flat: four octets per trip (one load), right to left; stops at a bad label or after `want` labels
         const uint32_t take = i - off < 4u ? i - off : 4u, raw = gb4(m + (i - 4));      // off >= 12: never before the message
+        const uint32_t lmb = take == 4u ? (uint32_t)(lm >> (i - 4 - off)) : (uint32_t)(lm << (4u - take));   // bit t: octet i - 4 + t is a length octet (one 64-bit shift per trip)
         #pragma unroll
         for (int t = 3; t >= 0; t--) {
             if ((uint32_t)(3 - t) < take && nlab < want && !stop) {
                 const uint32_t pos = i - 4 + t, b = (raw >> (8 * t)) & 0xffu;
-                if ((lm >> (pos - off)) & 1ull) {
+                if ((lmb >> t) & 1u) {
                     const uint64_t key = name_key(S1, S2, end - pos - 1);
                     #pragma unroll
                     for (int c = 0; c < DNS_MAX_CAND; c++) if ((uint32_t)c == nlab) { ck[c] = key; cpos[c] = pos; }
@@ -254,10 +255,11 @@ __device__ __noinline__ int dns_zone_select(const DevTables &T, P m, uint32_t ml
     for (int j = 0; j < 16; j++) {
         if (same && 4u * j < hit_len) {
             const uint32_t q = hit_off + 1 + 4u * j, raw = gb4(m + q);
+            const uint32_t lmw = (uint32_t)(lm >> ((q - off) & 63u));      // bit t: octet q + t is a length octet (q + 3 - off < 67: bits past 63 belong to octets past the name, masked below)
             uint32_t qw = 0;
             #pragma unroll
             for (int t = 0; t < 4; t++) {
-                const uint32_t ch = ((lm >> ((q + t - off) & 63u)) & 1ull) ? (uint32_t)'.' : lower((raw >> (8 * t)) & 0xffu);
+                const uint32_t ch = ((lmw >> t) & 1u) ? (uint32_t)'.' : lower((raw >> (8 * t)) & 0xffu);
                 if (4u * j + t < hit_len) qw |= ch << (8 * t);
             }
             same = qw == st.w[j];
