@@ -277,6 +277,43 @@ func (e *Engine) TotalsMerge(dBlocks unsafe.Pointer, nBlocks uint32) ([]Total, e
 }
 
 // StateSave / StateLoad: the pinned state shared with the ebpf-manager verbs (the bpffs analogue).
+// Hdr16 is clk_hdr16: the 16-byte compact ingest record (what the decision reads of an IPv4 header-only frame).
+type Hdr16 struct {
+	Src, Dst     uint32 // network order bytes loaded as native u32
+	Sport, Dport uint16 // host order
+	Proto, Kind  uint8  // Kind: 0 IPv4 record, 1 no socket event, 2 Src indexes the 64-byte slot of the frame in aux
+	_            uint16
+}
+
+// PackHdr16 turns slot-layout frames into records plus the whole frames a record cannot express (clk_pack_hdr16).
+func PackHdr16(pkts []byte, stride int) (recs []Hdr16, aux []byte, err error) {
+	n := len(pkts) / stride
+	recs = make([]Hdr16, n)
+	aux = make([]byte, 64*(n/8+1024))
+	for {
+		var nAux C.uint64_t
+		rc := C.clk_pack_hdr16((*C.uint8_t)(unsafe.Pointer(&pkts[0])), C.uint32_t(stride), C.uint64_t(n),
+			(*C.clk_hdr16)(unsafe.Pointer(&recs[0])), (*C.uint8_t)(unsafe.Pointer(&aux[0])), C.uint64_t(len(aux)/64), &nAux)
+		if rc == C.CLK_OK {
+			return recs, aux[:64*int(nAux)], nil
+		}
+		if rc != C.CLK_E2BIG || len(aux) >= 64*n {
+			return nil, nil, fmt.Errorf("clk_pack_hdr16: %s", C.GoString(C.clk_last_error(nil)))
+		}
+		aux = make([]byte, 64*n)
+	}
+}
+
+// ClassifyHdr16 classifies compact records (host buffers; 20 bytes per packet cross the host link instead of 68).
+func (e *Engine) ClassifyHdr16(recs []Hdr16, aux []byte, flags uint32, verdicts []uint32) error {
+	var ap *C.uint8_t
+	if len(aux) > 0 {
+		ap = (*C.uint8_t)(unsafe.Pointer(&aux[0]))
+	}
+	return e.err(C.clk_classify_hdr16(e.h, (*C.clk_hdr16)(unsafe.Pointer(&recs[0])), C.uint64_t(len(recs)), ap,
+		C.uint64_t(len(aux)/64), C.uint32_t(flags), (*C.uint32_t)(unsafe.Pointer(&verdicts[0]))))
+}
+
 // CommUniqueID is ncclGetUniqueId through the library: rank 0 calls it and hands the bytes to the other ranks.
 func CommUniqueID() ([]byte, error) {
 	buf := make([]byte, 256)
