@@ -857,7 +857,7 @@ __device__ __forceinline__ void payload_window(P pk, uint32_t avail, bool tcp, u
 #define VW_LISTS 6             // 0 generic, then NM_DNSQ .. NM_HTTP
 #define VW_QCAP 32             // a warp's queue is flushed (wholly) before it would overflow, and when it is full
 
-struct NameEnt { uint32_t idx, word, o16, units; };        // 16 B: packet index, phase-A word, frame offset and length in 16-byte units
+// a work-list entry is one uint4: {packet index, phase-A verdict word, frame offset / 16, frame length / 16}
 
 template <int kWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) k_varlen_head(const __grid_constant__ DevTables T, const uint8_t *__restrict__ pkts,

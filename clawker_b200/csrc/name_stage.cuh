@@ -10,31 +10,17 @@
 // open-addressing tables, and every hash hit is confirmed byte-for-byte against the stored name, so
 // results equal an exact string-keyed map lookup.
 //
-// Every parser is a template over the payload pointer type P:
-//   const uint8_t *  — the frame in global memory (read through ld.global.nc; generic / rare-frame kernels)
-//   SP               — the frame in SHARED memory (a 32-bit shared-window address; the chunk kernel stages
-//                      whole spans of frames with one bulk TMA copy and parses them from there)
+// Every parser is a template over the payload pointer type P.  The shipped kernels instantiate `const uint8_t *` (frames in
+// global memory, read through ld.global.nc / L1); a shared-memory window type was instantiated by the chunk-staging kernel
+// that was measured and dropped this round (profiles/r02_varlen_notes.md) — anything with `+ uint32_t`, gb() and gb4() works.
 // Table pointers (zones, server_names, names blob) are always global (L2-resident).
 
-struct SP { uint32_t a; };
-__device__ __forceinline__ SP operator+(SP p, uint32_t o) { return SP{ p.a + o }; }
-__device__ __forceinline__ SP operator-(SP p, uint32_t o) { return SP{ p.a - o }; }
-// volatile: never moved across the mbarrier wait that publishes the staged bytes (also volatile asm)
-__device__ __forceinline__ uint32_t gb(SP p) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(p.a)); return v; }
 __device__ __forceinline__ uint32_t gb(const uint8_t *p) { return __ldg(p); }
 template <class P> __device__ __forceinline__ uint32_t gbe16(P p) { return (gb(p) << 8) | gb(p + 1u); }
 __device__ __forceinline__ uint32_t lower(uint32_t c) { return (c - 'A' < 26u) ? c + 32u : c; }
 __device__ __forceinline__ bool zone_char(uint32_t c) { return (c - 'a' < 26u) || (c - '0' < 10u) || c == '_' || c == '-'; }
 
-// Four payload bytes p[0..3] as one little-endian word.  Shared memory: two aligned 32-bit loads and a funnel shift
-// (a few bytes either side of the frame may be touched; they lie inside the CTA's staging buffer).
-__device__ __forceinline__ uint32_t gb4(SP p)
-{
-    uint32_t lo, hi; const uint32_t a = p.a & ~3u;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(hi) : "r"(a));
-    return __funnelshift_r(lo, hi, (p.a & 3u) * 8u);
-}
+// Four payload bytes p[0..3] as one little-endian word (the bytes share a line: one L1 access after the first).
 __device__ __forceinline__ uint32_t gb4(const uint8_t *p) { return gb(p) | (gb(p + 1) << 8) | (gb(p + 2) << 16) | (gb(p + 3) << 24); }
 
 // Names of the zone / server_names / virtual-host tables in the blob: lower-case bytes, 16-byte aligned, zero padded to a
