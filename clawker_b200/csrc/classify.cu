@@ -880,13 +880,15 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) k_varlen_head(const _
     for (int k = 0; k < VW_LISTS; k++) qn[k] = 0;
 
     // the whole queue k of this warp -> global list k: one atomic, one coalesced store of 16-byte entries
-    // (a macro, not a lambda taking k: the queue lengths must stay in registers)
-#define VW_FLUSH(k) do { \
-        const uint32_t take_ = qn[k]; uint32_t base_ = 0; \
-        if (lane == 0) base_ = atomicAdd(&cnt[k], take_); \
-        base_ = __shfl_sync(0xffffffffu, base_, 0); \
-        if (lane < take_ && base_ + lane < cap) ents[(size_t)(k) * cap + base_ + lane] = queue[(k) * VW_QCAP + lane]; \
-        qn[k] = 0; __syncwarp(); } while (0)
+    auto flush = [&](int k) {
+        const uint32_t take = qn[k];
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cnt[k], take);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < take && base + lane < cap) ents[(size_t)k * cap + base + lane] = queue[k * VW_QCAP + lane];
+        qn[k] = 0;
+        __syncwarp();
+    };
 
     // Software pipeline, two tiles deep: while tile t is classified, the header words of tile t + W and the offsets of
     // tile t + 2W are in flight (a warp keeps ~3 KB of loads outstanding; 16 warps cover the DRAM latency of an SM).
@@ -928,18 +930,17 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) k_varlen_head(const _
             const unsigned m = __ballot_sync(0xffffffffu, kind == (uint32_t)k);
             if (m) {
                 const uint32_t c = __popc(m);
-                if (qn[k] + c > VW_QCAP) VW_FLUSH(k);
+                if (qn[k] + c > VW_QCAP) flush(k);
                 if (kind == (uint32_t)k) queue[k * VW_QCAP + qn[k] + __popc(m & ((1u << lane) - 1u))] = make_uint4(first + i, w, o0, o1 - o0);
                 qn[k] += c;
                 __syncwarp();
-                if (qn[k] == VW_QCAP) VW_FLUSH(k);
+                if (qn[k] == VW_QCAP) flush(k);
             }
         }
         o0 = o0n; o1 = o1n; w3 = w3n; q1 = q1n; q2 = q2n; o0n = o0f; o1n = o1f;
     }
     #pragma unroll
-    for (int k = 0; k < VW_LISTS; k++) if (qn[k]) VW_FLUSH(k);
-#undef VW_FLUSH
+    for (int k = 0; k < VW_LISTS; k++) if (qn[k]) flush(k);
     if (do_metrics) metric_cta_flush(T, ag);
 }
 

@@ -21,7 +21,18 @@ __device__ __forceinline__ uint32_t lower(uint32_t c) { return (c - 'A' < 26u) ?
 __device__ __forceinline__ bool zone_char(uint32_t c) { return (c - 'a' < 26u) || (c - '0' < 10u) || c == '_' || c == '-'; }
 
 // Four payload bytes p[0..3] as one little-endian word (the bytes share a line: one L1 access after the first).
-__device__ __forceinline__ uint32_t gb4(const uint8_t *p) { return gb(p) | (gb(p + 1) << 8) | (gb(p + 2) << 16) | (gb(p + 3) << 24); }
+__device__ __forceinline__ uint32_t gb4(const uint8_t *p) { return gb(p) | (gb(p + 1) << 8) | (gb(p + 2) << 16) | (gb(p + 3) << 24); }   // (two aligned word loads + a funnel shift measured slower: the alignment arithmetic costs more than it saves)
+
+// p[0 .. nvalid) (nvalid >= 1) as a little-endian word, never touching p[nvalid] and beyond when fewer than four bytes are left
+template <class P>
+__device__ __forceinline__ uint32_t gb4n(P p, uint32_t nvalid)
+{
+    if (nvalid >= 4u) return gb4(p);
+    uint32_t v = gb(p);
+    if (nvalid > 1u) v |= gb(p + 1u) << 8;
+    if (nvalid > 2u) v |= gb(p + 2u) << 16;
+    return v;
+}
 
 // Names of the zone / server_names / virtual-host tables in the blob: lower-case bytes, 16-byte aligned, zero padded to a
 // multiple of 16; NameSlot.str_off = length << 24 | offset / 16.
@@ -195,28 +206,34 @@ __device__ __noinline__ int dns_zone_select(const DevTables &T, P m, uint32_t ml
     for (int c = 0; c < DNS_MAX_CAND; c++) { ck[c] = 0; cpos[c] = 0; }
     uint32_t S1 = 0, S2 = 0, nlab = 0;
     const uint32_t want = (simple && T.zone_slots != nullptr) ? T.zone_max_labels : 0u;
+    // Label by label from the right, every lane at ITS label boundary at the same time (the boundary work — key, candidate
+    // slot, the '.' — runs once per label with the lanes together, not once per octet position with whoever happens to have
+    // a length octet there); inside a label four octets per load, right to left.  `r` = end of the current label (exclusive),
+    // its length octet is the highest bit of lm below r.
     bool stop = false;
-    for (uint32_t i = end; i > off && nlab < want && !stop;) {   // flat: four octets per trip (one load), right to left; stops at a bad label or after `want` labels
-        const uint32_t take = i - off < 4u ? i - off : 4u, raw = gb4(m + (i - 4));      // off >= 12: never before the message
-        const uint32_t lmb = take == 4u ? (uint32_t)(lm >> (i - 4 - off)) : (uint32_t)(lm << (4u - take));   // bit t: octet i - 4 + t is a length octet (one 64-bit shift per trip)
-        #pragma unroll
-        for (int t = 3; t >= 0; t--) {
-            if ((uint32_t)(3 - t) < take && nlab < want && !stop) {
-                const uint32_t pos = i - 4 + t, b = (raw >> (8 * t)) & 0xffu;
-                if ((lmb >> t) & 1u) {
-                    const uint64_t key = name_key(S1, S2, end - pos - 1);
-                    #pragma unroll
-                    for (int c = 0; c < DNS_MAX_CAND; c++) if ((uint32_t)c == nlab) { ck[c] = key; cpos[c] = pos; }
-                    nlab++;
-                    S1 = '.' + NAME_B1 * S1; S2 = '.' + NAME_B2 * S2;
-                } else {
-                    const uint32_t ch = lower(b);
-                    if (!zone_char(ch)) stop = true;            // no zone contains this label, nor any longer suffix
-                    else { S1 = ch + NAME_B1 * S1; S2 = ch + NAME_B2 * S2; }
+    uint32_t r = end;
+    while (nlab < want && r > off && !stop) {
+        const uint32_t lp = off + (63u - (uint32_t)__clzll((long long)(lm & ((1ull << (r - off)) - 1ull))));   // r > off: lm has a bit below r (the first length octet sits at off)
+        for (uint32_t i = r; i > lp + 1u;) {                  // the label's octets lp + 1 .. r - 1
+            const uint32_t take = i - (lp + 1u) < 4u ? i - (lp + 1u) : 4u, raw = gb4(m + (i - 4));      // off >= 12: never before the message
+            #pragma unroll
+            for (int t = 3; t >= 0; t--) {
+                if ((uint32_t)(3 - t) < take) {
+                    const uint32_t ch = lower((raw >> (8 * t)) & 0xffu);
+                    stop |= !zone_char(ch);                   // no zone contains this label, nor any longer suffix
+                    S1 = ch + NAME_B1 * S1; S2 = ch + NAME_B2 * S2;
                 }
             }
+            i -= take;
         }
-        i -= take;
+        if (!stop) {
+            const uint64_t key = name_key(S1, S2, end - lp - 1);
+            #pragma unroll
+            for (int c = 0; c < DNS_MAX_CAND; c++) if ((uint32_t)c == nlab) { ck[c] = key; cpos[c] = lp; }
+            nlab++;
+            S1 = '.' + NAME_B1 * S1; S2 = '.' + NAME_B2 * S2;
+        }
+        r = lp;
     }
     __syncwarp(mask);
     NamePair pr[DNS_MAX_CAND];
@@ -240,7 +257,7 @@ __device__ __noinline__ int dns_zone_select(const DevTables &T, P m, uint32_t ml
     #pragma unroll
     for (int j = 0; j < 16; j++) {
         if (same && 4u * j < hit_len) {
-            const uint32_t q = hit_off + 1 + 4u * j, raw = gb4(m + q);
+            const uint32_t q = hit_off + 1 + 4u * j, raw = gb4n(m + q, end - q);                    // q < end here
             const uint32_t lmw = (uint32_t)(lm >> ((q - off) & 63u));      // bit t: octet q + t is a length octet (q + 3 - off < 67: bits past 63 belong to octets past the name, masked below)
             uint32_t qw = 0;
             #pragma unroll
@@ -408,7 +425,7 @@ __device__ __forceinline__ bool sni_match(const DevTables &T, P host, uint32_t n
     uint32_t S1 = 0, S2 = 0, ndot = 0; bool nul = false;
     const uint32_t want = T.sni_max_dots;
     for (uint32_t i = n; i > 0;) {                           // flat: four bytes per trip (one load), right to left
-        const uint32_t take = i < 4u ? i : 4u, raw = i >= 4u ? gb4(host + (i - 4)) : gb4(host) << (8u * (4u - i));   // byte `pos` of the name sits at bits 8 * (pos - (i - 4))
+        const uint32_t take = i < 4u ? i : 4u, raw = i >= 4u ? gb4(host + (i - 4)) : gb4n(host, i) << (8u * (4u - i));   // byte `pos` of the name sits at bits 8 * (pos - (i - 4))
         #pragma unroll
         for (int t = 3; t >= 0; t--) {
             if ((uint32_t)(3 - t) < take) {
@@ -448,7 +465,7 @@ __device__ __forceinline__ bool sni_match(const DevTables &T, P host, uint32_t n
     #pragma unroll
     for (int j = 0; j < 16; j++) {
         if (same && 4u * j < cl) {
-            const uint32_t raw = gb4(host + (from + 4u * j));
+            const uint32_t raw = gb4n(host + (from + 4u * j), n - (from + 4u * j));
             uint32_t qw = 0;
             #pragma unroll
             for (int t = 0; t < 4; t++) if (4u * j + t < cl) qw |= lower((raw >> (8 * t)) & 0xffu) << (8 * t);
