@@ -183,11 +183,13 @@ def bind_to_gpu_numa(local: int) -> dict:
     return info
 
 
-def make_batch(workload: str, rank: int):
+def make_batch(workload: str, rank: int, untiled: bool = False):
     """Synthetic capture of the named shape: `gen` unique packets (tiled to n on the device; HBM does not care —
-    the tiling is stated in config.synthetic and --untiled generates every packet)."""
+    the tiling is stated in config.synthetic and --untiled generates every packet of the batch)."""
     from clawker_b200 import capture
-    spec = workload_spec(workload)
+    spec = dict(workload_spec(workload))
+    if untiled:
+        spec["gen"] = spec["n"]
     w = capture.make_workload(spec["cfg"])
     if spec["layout"] == "slots":
         return w, (capture.gen_slots(w, spec["gen"], seed=2 + 1000 * rank, **spec.get("mix", {})), None), spec
@@ -372,7 +374,7 @@ def measure(args, workload: str, full: bool) -> dict:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    w, batch, spec = make_batch(workload, rank)
+    w, batch, spec = make_batch(workload, rank, untiled=args.untiled)
     pk, offs = batch
     varlen = offs is not None
     gen = batch_packets(batch)
@@ -707,6 +709,7 @@ def main():
     ap.add_argument("--also", default=None, help="comma-separated workloads measured in the same run and reported under \"also\" (default: c2 next to c3)")
     ap.add_argument("--sweep", action="store_true", help="c5 rule-table sweep 2^4..2^20 entries: value and roofline fraction per size")
     ap.add_argument("--packets", type=int, default=0, help="override packets per GPU per step")
+    ap.add_argument("--untiled", action="store_true", help="generate every packet of the batch instead of tiling `gen` unique ones (slow to generate; shows the tiling does not matter)")
     ap.add_argument("--seconds", type=float, default=3.0, help="length of the sustained leg (0 = skip)")
     ap.add_argument("--ref-sample-seconds", type=float, default=2.0, help="length of one CPU sample of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
