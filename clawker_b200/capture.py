@@ -469,10 +469,10 @@ def build_varlen(frames: list[bytes]) -> tuple[np.ndarray, np.ndarray]:
     return blob, (offs // 16).astype(np.uint32)
 
 
-def frame(src: int, dst: int, proto: int, sport: int, dport: int, payload: bytes = b"", tcp_flags: int = 0x18) -> bytes:
+def frame(src: int, dst: int, proto: int, sport: int, dport: int, payload: bytes = b"", tcp_flags: int = 0x18, seq: int = 1) -> bytes:
     """One Ethernet II / IPv4 / TCP|UDP frame around `payload`."""
     if proto == 6:
-        l4 = struct.pack(">HHIIBBHHH", sport, dport, 1, 1, 0x50, tcp_flags, 65535, 0, 0)
+        l4 = struct.pack(">HHIIBBHHH", sport, dport, seq & 0xffffffff, 1, 0x50, tcp_flags, 65535, 0, 0)
     elif proto == 17:
         l4 = struct.pack(">HHHH", sport, dport, 8 + len(payload), 0)
     else:

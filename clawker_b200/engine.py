@@ -90,6 +90,11 @@ def lib() -> C.CDLL:
         "clk_pcap_pack": (i32, [C.c_char_p, C.POINTER(u64), vp, u64, vp, u64, C.POINTER(u64)]),
         "clk_classify_pcap": (i32, [vp, C.c_char_p, u32, vp, u64, C.POINTER(u64)]),
         "clk_pcap_last_error": (C.c_char_p, []),
+        "clk_afpacket_open": (i32, [C.c_char_p, u32, C.POINTER(vp)]),
+        "clk_afpacket_read": (i32, [vp, vp, u64, vp, u64, i32, C.POINTER(u64)]),
+        "clk_afpacket_close": (i32, [vp]),
+        "clk_tcp_coalesce": (i32, [vp, vp, u64, vp, u64, vp, C.POINTER(u64)]),
+        "clk_ingest_last_error": (C.c_char_p, []),
         "clk_state_save": (i32, [vp, C.c_char_p]),
         "clk_state_load": (i32, [vp, C.c_char_p]),
         "clk_totals_rows": (i32, [vp, C.POINTER(u32)]),
@@ -121,7 +126,47 @@ EXPORTS = ["clk_abi_version", "clk_strerror", "clk_last_error", "clk_engine_crea
            "clk_classify_varlen", "clk_classify_slots_dev", "clk_classify_varlen_dev", "clk_classify_events", "clk_pack_hdr16", "clk_classify_hdr16", "clk_classify_hdr16_dev",
            "clk_dns_answers", "clk_counters_read", "clk_counters_read_global", "clk_counters_reset", "clk_counters_block_rows",
            "clk_counters_export", "clk_counters_import", "clk_totals_rows", "clk_totals_export", "clk_totals_merge", "clk_comm_unique_id", "clk_comm_init", "clk_comm_destroy", "clk_comm_info",
-           "clk_allgather_counters", "clk_totals_read_global", "clk_allgather_metrics", "clk_state_save", "clk_state_load", "clk_pcap_pack", "clk_classify_pcap", "clk_pcap_last_error", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
+           "clk_allgather_counters", "clk_totals_read_global", "clk_allgather_metrics", "clk_state_save", "clk_state_load", "clk_pcap_pack", "clk_classify_pcap", "clk_pcap_last_error", "clk_afpacket_open", "clk_afpacket_read", "clk_afpacket_close", "clk_tcp_coalesce", "clk_ingest_last_error", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
+
+
+class PacketRing:
+    """AF_PACKET / TPACKET_V3 receive ring on one interface (clk_afpacket_*): read() returns (blob, offs16) in the varlen layout."""
+
+    def __init__(self, ifname: str, ring_mib: int = 0):
+        self.L, self.h = lib(), C.c_void_p()
+        rc = self.L.clk_afpacket_open(ifname.encode(), ring_mib, C.byref(self.h))
+        if rc:
+            raise ClkError(rc, self.L.clk_ingest_last_error().decode())
+
+    def read(self, cap_bytes: int = 16 << 20, cap_frames: int = 1 << 16, timeout_ms: int = 100):
+        blob, offs, n = np.zeros(cap_bytes, dtype=np.uint8), np.zeros(cap_frames + 1, dtype=np.uint32), C.c_uint64()
+        rc = self.L.clk_afpacket_read(self.h, blob.ctypes.data, cap_bytes, offs.ctypes.data, cap_frames, timeout_ms, C.byref(n))
+        if rc:
+            raise ClkError(rc, self.L.clk_ingest_last_error().decode())
+        return blob[: int(offs[n.value]) * 16], offs[: n.value + 1]
+
+    def close(self):
+        if self.h:
+            self.L.clk_afpacket_close(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def tcp_coalesce(blob: np.ndarray, offs16: np.ndarray):
+    """clk_tcp_coalesce: (blob, offs16, n_merged) with split ClientHellos / HTTP request heads folded into their first segment."""
+    L = lib()
+    blob, offs16 = np.ascontiguousarray(blob, dtype=np.uint8), np.ascontiguousarray(offs16, dtype=np.uint32)
+    n = offs16.size - 1
+    out, oo, merged = np.zeros(2 * blob.size + 64, dtype=np.uint8), np.zeros(n + 1, dtype=np.uint32), C.c_uint64()
+    rc = L.clk_tcp_coalesce(blob.ctypes.data, offs16.ctypes.data, n, out.ctypes.data, out.size, oo.ctypes.data, C.byref(merged))
+    if rc:
+        raise ClkError(rc, L.clk_ingest_last_error().decode())
+    return out[: int(oo[n]) * 16], oo, merged.value
 
 
 def pcap_pack(path: str, cap_bytes: int = 64 << 20, cap_frames: int = 1 << 20):

@@ -383,3 +383,48 @@ func (e *Engine) ClassifyPcap(path string, flags uint32) ([]uint32, error) {
 	}
 	return out[:int(n)], nil
 }
+
+// Ring is an AF_PACKET / TPACKET_V3 receive ring on one interface (clk_afpacket_*): live ingest into the varlen layout.
+type Ring struct{ h *C.clk_ring }
+
+func OpenRing(ifname string, ringMiB uint32) (*Ring, error) {
+	p := C.CString(ifname)
+	defer C.free(unsafe.Pointer(p))
+	var h *C.clk_ring
+	if rc := C.clk_afpacket_open(p, C.uint32_t(ringMiB), &h); rc != C.CLK_OK {
+		return nil, fmt.Errorf("clawker_gpu: %s (%d)", C.GoString(C.clk_ingest_last_error()), int(rc))
+	}
+	return &Ring{h}, nil
+}
+
+// Read drains ready blocks into blob / offs16 (len(offs16) - 1 frames at most) and returns the number of frames.
+func (r *Ring) Read(blob []byte, offs16 []uint32, timeoutMs int) (int, error) {
+	if len(blob) == 0 || len(offs16) < 2 {
+		return 0, fmt.Errorf("clawker_gpu: empty buffers")
+	}
+	var n C.uint64_t
+	rc := C.clk_afpacket_read(r.h, (*C.uint8_t)(unsafe.Pointer(&blob[0])), C.uint64_t(len(blob)), (*C.uint32_t)(unsafe.Pointer(&offs16[0])),
+		C.uint64_t(len(offs16)-1), C.int(timeoutMs), &n)
+	if rc != C.CLK_OK {
+		return 0, fmt.Errorf("clawker_gpu: %s (%d)", C.GoString(C.clk_ingest_last_error()), int(rc))
+	}
+	return int(n), nil
+}
+
+func (r *Ring) Close() { C.clk_afpacket_close(r.h); r.h = nil }
+
+// TCPCoalesce folds the continuation segments of split ClientHellos / HTTP request heads into their first segment
+// (one output frame per input frame); out must hold 2 x len(blob).
+func TCPCoalesce(blob []byte, offs16 []uint32, out []byte, outOffs16 []uint32) (merged uint64, err error) {
+	n := len(offs16) - 1
+	if n <= 0 || len(out) == 0 || len(outOffs16) < len(offs16) {
+		return 0, fmt.Errorf("clawker_gpu: bad buffers")
+	}
+	var m C.uint64_t
+	rc := C.clk_tcp_coalesce((*C.uint8_t)(unsafe.Pointer(&blob[0])), (*C.uint32_t)(unsafe.Pointer(&offs16[0])), C.uint64_t(n),
+		(*C.uint8_t)(unsafe.Pointer(&out[0])), C.uint64_t(len(out)), (*C.uint32_t)(unsafe.Pointer(&outOffs16[0])), &m)
+	if rc != C.CLK_OK {
+		return 0, fmt.Errorf("clawker_gpu: %s (%d)", C.GoString(C.clk_ingest_last_error()), int(rc))
+	}
+	return uint64(m), nil
+}

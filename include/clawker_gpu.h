@@ -435,6 +435,29 @@ int clk_classify_pcap(clk_engine *e, const char *path, uint32_t flags, uint32_t 
                       uint64_t cap, uint64_t *n);
 const char *clk_pcap_last_error(void);
 
+/* ---- live ingest and TCP reassembly ------------------------- */
+/* An AF_PACKET / TPACKET_V3 receive ring on one interface (needs CAP_NET_RAW; ring_mib = ring size in
+ * MiB, 0 = 64).  clk_afpacket_read waits up to timeout_ms for the first ready block, then drains ready
+ * blocks into the varlen layout of clk_classify_varlen until a capacity runs out (a partly drained
+ * block is resumed by the next call): *n_frames frames, offs16[0 .. n_frames] set.  No reference
+ * counterpart: the reference's hooks see sockets (clawker.c:62-362), never frames. */
+typedef struct clk_ring clk_ring;
+int clk_afpacket_open(const char *ifname, uint32_t ring_mib, clk_ring **out);
+int clk_afpacket_read(clk_ring *r, uint8_t *blob, uint64_t cap_bytes, uint32_t *offs16,
+                      uint64_t cap_frames, int timeout_ms, uint64_t *n_frames);
+int clk_afpacket_close(clk_ring *r);
+/* TCP reassembly for the name stage.  Envoy's tls_inspector and HTTP codec buffer a connection until
+ * the ClientHello / request head is complete (envoy.go:299-306 listener filters); a per-packet
+ * classifier answers N/A for a first segment that does not hold all of it.  This pass appends the
+ * in-order continuation segments of the same flow (src, dst, sport, dport; next sequence number) to
+ * the first segment's frame and empties the continuation segments (headers kept, payload dropped:
+ * name verdict N/A), so the output has ONE FRAME PER INPUT FRAME and verdict arrays stay aligned with
+ * the capture.  out_blob: 2 x the input bytes is always enough.  *n_merged = segments folded.
+ * Errors from this group: clk_ingest_last_error(). */
+int clk_tcp_coalesce(const uint8_t *blob, const uint32_t *offs16, uint64_t n, uint8_t *out_blob,
+                     uint64_t out_cap_bytes, uint32_t *out_offs16, uint64_t *n_merged);
+const char *clk_ingest_last_error(void);
+
 /* ---- pinned state ------------------------------------------- */
 /* The reference keeps its maps pinned in bpffs (/sys/fs/bpf/clawker, manager.go:27-38,111-133) so that
  * each `ebpf-manager <verb>` process can open, change and leave them (cmd/main.go:84-143).  The GPU
