@@ -625,7 +625,7 @@ def measure(args, workload: str, full: bool) -> dict:
                          "algorithmic_bytes_per_packet": round(bytes_per_packet, 2)},
             "e2e": {"value": round(world * n_e2e / e2e_ms / 1e3, 1), "unit": "Mpackets/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": n_e2e * 4, "packets_per_step": n_e2e, "ms_per_step": round(e2e_ms, 3),
-                    "bytes_per_packet_over_pcie": round((h2d_bytes + n_e2e * 4) / n_e2e, 1), "verdict_mismatches": e2e_parity,
+                    "bytes_per_packet_over_pcie": round((h2d_bytes + n_e2e * 4) / n_e2e, 1), "h2d_GBps_per_gpu": round(h2d_bytes / e2e_ms / 1e6, 1), "verdict_mismatches": e2e_parity,
                     "path": ("clk_classify_varlen" if varlen else "clk_classify_slots") + " (pinned host buffers, 3-stream chunked H2D/kernel/D2H)"},
             "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
             "metrics": {"max_entries": args.metrics_capacity, "rows": int(e.counters().size), "dropped_increments": int(e.stats().metrics_dropped)},
@@ -633,7 +633,7 @@ def measure(args, workload: str, full: bool) -> dict:
         if e2e_compact:
             out["e2e_compact"] = {"value": round(world * n_e2e / e2e_compact["ms"] / 1e3, 1), "unit": "Mpackets/s", "h2d_bytes_per_step": e2e_compact["h2d"],
                                   "d2h_bytes_per_step": n_e2e * 4, "packets_per_step": n_e2e, "ms_per_step": round(e2e_compact["ms"], 3),
-                                  "bytes_per_packet_over_pcie": round((e2e_compact["h2d"] + n_e2e * 4) / n_e2e, 1), "verdict_mismatches": e2e_compact["bad"],
+                                  "bytes_per_packet_over_pcie": round((e2e_compact["h2d"] + n_e2e * 4) / n_e2e, 1), "h2d_GBps_per_gpu": round(e2e_compact["h2d"] / e2e_compact["ms"] / 1e6, 1), "verdict_mismatches": e2e_compact["bad"],
                                   "aux_slots": e2e_compact["aux_slots"], "pack_mpps_one_thread": e2e_compact["pack_mpps_one_thread"],
                                   "path": "clk_classify_hdr16: 16-byte ingest records (clk_pack_hdr16, packed by the capture front end outside the timed region) + whole frames for what a record cannot express"}
         if sustained:

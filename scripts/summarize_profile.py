@@ -6,7 +6,8 @@ launch_csv = sys.argv[5] if len(sys.argv) > 5 and sys.argv[5] != '-' else None
 bpp = float(sys.argv[6]) if len(sys.argv) > 6 else 68.0
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(root, "profiles"); os.makedirs(out_dir, exist_ok=True)
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+kfilter = ["--kernel-name", "regex:" + kern.split("::")[-1].split("<")[0].split(" ")[0], "--launch-count", "1"]      # a report may hold several kernels: the first launch of this one
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + kfilter, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw))); hdr, units, vals = rows[0], rows[1], rows[2]
 def g(name):
     return (vals[hdr.index(name)], units[hdr.index(name)]) if name in hdr else (None, None)
@@ -23,12 +24,15 @@ rd, wr = g("dram__bytes_read.sum"), g("dram__bytes_write.sum")
 dur, du = g("gpu__time_duration.sum")
 dur_us = float(dur.replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3, "usecond": 1, "msecond": 1e3, "nsecond": 1e-3}.get(du, 1)
 traffic = to_bytes(*rd) + to_bytes(*wr)
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + kfilter, capture_output=True, text=True).stdout
 srows = list(csv.reader(io.StringIO(src))); sh = srows[1]
 cols = [i for i, h in enumerate(sh) if h.startswith("stall_") and "Not Issued" not in h]
 st = collections.Counter()
 ie, at = sh.index("Instructions Executed"), sh.index("Avg. Threads Executed"); n_inst = 0
-for r in srows[2:]:
+body = srows[2:]
+for j, r in enumerate(body):                  # (the source page repeats the listing once per view: keep the first copy)
+    if j and r[:1] == body[0][:1] and r[1:2] == body[0][1:2]: body = body[:j]; break
+for r in body:
     for i in cols:
         try: st[sh[i]] += int(r[i])
         except Exception: pass
