@@ -23,6 +23,20 @@
 #include "dev_tables.h"
 #include "classify.h"
 
+// The warp index as a value the compiler can prove warp-uniform (a shuffle from a fixed lane): everything derived from it —
+// tile / barrier / queue addresses, loop counters — can then live in uniform registers and the TMA / mbarrier sequences need no
+// per-lane election loop.
+#ifndef CLK_ELECT
+#define CLK_ELECT 1
+#endif
+#ifndef CLK_UWARP
+#define CLK_UWARP 1
+#endif
+#if CLK_UWARP
+#define UNIFORM_WARP_IDX() ((uint32_t)__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0))
+#else
+#define UNIFORM_WARP_IDX() (threadIdx.x >> 5)
+#endif
 namespace clk {
 
 // ------------------------------------------------------------------------------------------------
@@ -49,6 +63,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// One lane of a converged warp (elect.sync): the compiler keeps the code under it on the uniform datapath (no per-lane
+// election loop around UTMALDG / the mbarrier arrive) when its operands are warp-uniform.
+__device__ __forceinline__ bool elect_one()
+{
+#if CLK_ELECT
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+    return p != 0;
+#else
+    return (threadIdx.x & 31u) == 0;
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
 {
@@ -584,8 +610,9 @@ __device__ __forceinline__ void cta_prologue(const DevTables &T, uint8_t *smem, 
 {
     ag.keys = (unsigned long long *)(smem + L.agg_keys);
     ag.counts = (unsigned int *)(smem + L.agg_counts); ag.dropped = 0u; ag.mask = agg_slots - 1;
-    ag.log_keys = (unsigned long long *)(smem + L.mlog) + (threadIdx.x >> 5) * MLOG_CAP;
-    ag.log_cnts = (unsigned int *)(smem + L.mlog + (blockDim.x >> 5) * MLOG_CAP * 8) + (threadIdx.x >> 5) * MLOG_CAP; ag.log_n = 0;
+    const uint32_t wu = UNIFORM_WARP_IDX();
+    ag.log_keys = (unsigned long long *)(smem + L.mlog) + wu * MLOG_CAP;
+    ag.log_cnts = (unsigned int *)(smem + L.mlog + (blockDim.x >> 5) * MLOG_CAP * 8) + wu * MLOG_CAP; ag.log_n = 0;
     for (uint32_t i = threadIdx.x; i < agg_slots; i += blockDim.x) { ag.keys[i] = 0ull; ag.counts[i] = 0u; }
     uint64_t *bars = (uint64_t *)(smem + L.bars);
     tb.ep = T.ep_slots; tb.ep_mask = T.ep_mask; tb.ep_shift = T.ep_shift; tb.rowq = T.ep_rowq;
@@ -740,7 +767,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
     const SmemLayout L = smem_layout(T, FAST_WARPS * kStages * WTILE_BYTES, FAST_WARPS * WQ_CAP * 4, FAST_WARPS * kStages, agg_slots, FAST_WARPS);
     Tabs tb; MetricAgg ag;
     cta_prologue<kAllStaged>(T, smem, L, FAST_WARPS * kStages, tb, ag, agg_slots);
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = UNIFORM_WARP_IDX();
     uint64_t *bars = (uint64_t *)(smem + L.bars) + warp * kStages;
     uint8_t *tiles = smem + L.tiles + warp * (kStages * WTILE_BYTES);
     uint32_t *queue = (uint32_t *)(smem + L.queue) + warp * WQ_CAP;
@@ -749,7 +776,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
     const bool do_metrics = !(flags & CLK_F_NO_METRICS);
     __syncthreads();                                         // tables staged, aggregation table zeroed, barriers initialised
 
-    if (lane == 0) {
+    if (elect_one()) {
         for (int s = 0; s < kStages; s++) {
             uint32_t t = gw + (uint32_t)s * W;
             if (t < n_tiles) { mbar_expect_tx(&bars[s], WTILE_BYTES); tma_load_2d(tiles + s * WTILE_BYTES, &map, &bars[s], 0, (int)(t << 5)); }
@@ -770,7 +797,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
         const uint4 q1 = *(const uint4 *)(slot + ((1u ^ x) << 4));
         const uint2 q2 = *(const uint2 *)(slot + ((2u ^ x) << 4));
         __syncwarp();                                                        // every lane holds its header words
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t tn = t + (uint32_t)kStages * W;
             if (tn < n_tiles) { fence_proxy_async(); mbar_expect_tx(&bars[s], WTILE_BYTES); tma_load_2d(tiles + s * WTILE_BYTES, &map, &bars[s], 0, (int)(tn << 5)); }
         }
@@ -866,7 +893,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) k_varlen_head(const _
     Tabs tb; MetricAgg ag;
     cta_prologue<false>(T, smem, L, 0, tb, ag);
     __syncthreads();
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = UNIFORM_WARP_IDX();
     uint4 *queue = (uint4 *)(smem + L.queue) + warp * (VW_LISTS * VW_QCAP);
     const uint32_t n_tiles = (n + 31u) >> 5;
     const uint32_t gw = blockIdx.x * kWarps + warp, W = gridDim.x * kWarps;

@@ -3,7 +3,13 @@ usage: stall_by_line.py <cubin> <kernel-substring> <ncu_source.csv> [top]"""
 import re, csv, collections, subprocess, os, sys
 cubin, kern, prof = sys.argv[1:4]; top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.split("\n")
-start = next(i for i, l in enumerate(dis) if l.startswith("\t.section") and kern in l and ".text." in l)
+starts = [i for i, l in enumerate(dis) if l.startswith("\t.section") and kern in l and ".text." in l]
+n_prof = sum(1 for r in csv.reader(open(sys.argv[3])) if r and r[0].startswith("0x"))
+def n_inst(st):
+    en = next((i for i in range(st + 1, len(dis)) if dis[i].startswith("\t.section")), len(dis))
+    return sum(1 for l in dis[st:en] if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l))
+# several instantiations may match the substring: the profiled one has as many instructions as the profile has rows (the page may list it twice)
+start = min(starts, key=lambda st: min(abs(n_inst(st) - n_prof), abs(2 * n_inst(st) - n_prof)))
 end = next((i for i in range(start + 1, len(dis)) if dis[i].startswith("\t.section")), len(dis))
 cur = None; insts = []
 for l in dis[start:end]:
