@@ -799,6 +799,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, kMinBlocks) k_slots_fast(cons
         __syncwarp();                                                        // every lane holds its header words
         if (elect_one()) {
             uint32_t tn = t + (uint32_t)kStages * W;
+            // The fence is load-bearing: it makes the elected lane wait until the warp's ld.shared of this tile have RETURNED
+            // before the async proxy may overwrite the stage (__syncwarp alone only orders their issue).  Measured without it
+            // (round 2): verdict words of the checked copies still equal, but 1-2 stray metrics_map rows per 10 M packets —
+            // a header read after the refill had landed — for +0.3 %.
             if (tn < n_tiles) { fence_proxy_async(); mbar_expect_tx(&bars[s], WTILE_BYTES); tma_load_2d(tiles + s * WTILE_BYTES, &map, &bars[s], 0, (int)(tn << 5)); }
         }
         const uint32_t i = (t << 5) + lane;
