@@ -347,6 +347,11 @@ def check_parity(e, w, batch, d_v, n: int, gen: int, varlen: bool, flags: int, r
         mism += int((got[:k] != want[:k]).sum())
         checked += k
     out = {"checked": checked, "mismatches": mism, "rate": round(1.0 - mism / max(1, checked), 9), "oracle": "ref" if kind == "reference" else "port"}
+    if reps > 1:                                                   # every other copy of the unique packets, on the device: equal to the first copy word for word
+        whole = d_v[:reps * gen].view(reps, gen)
+        out["copies_checked"] = reps                               # the whole benched batch: reps x gen verdict words
+        out["copy_mismatches"] = int((whole != whole[0:1]).sum().item())
+        out["rate"] = round(1.0 - (mism + out["copy_mismatches"]) / float(reps * gen), 9)
     if n == reps * gen:
         e.counters_reset()
         run_step()
