@@ -73,7 +73,7 @@ struct clk_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t pipe[3] = { nullptr, nullptr, nullptr };
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_recorded = false;   // ev_recorded: both events have been recorded at least once
     uint32_t max_containers = 256, max_dns = 16384, max_routes = 8192, max_metrics = 16384, max_cidrs = 1u << 20, reserved_sms = 0;
 
     // host shadow tables (the BPF maps)
@@ -879,7 +879,7 @@ try {
     CUDA_TRY(e, sc.ensure((n + (1u << 20)) * 4));              // per-CTA regions (packets of the CTA's tiles); grows only for larger batches
     const char *err = launch_slots(e->T, d_pkts, stride, n, flags, (uint32_t *)d_verdicts, st, e->loader, e->stages,
                                    (uint32_t *)sc.p + 2, (uint32_t *)sc.p, &li);
-    if (!stream) cudaEventRecord(e->ev1, st);
+    if (!stream) { cudaEventRecord(e->ev1, st); e->ev_recorded = true; }
     return finish_launch(e, err, li);
 } CLK_GUARD_INT(e)
 
@@ -896,7 +896,7 @@ try {
     const VarlenCtx *vc = nullptr;
     rc = varlen_ctx(e, st, n, &vc); if (rc) return rc;
     const char *err = launch_varlen(e->T, d_pkts, (const uint32_t *)d_offs16, n, flags, (uint32_t *)d_verdicts, st, vc, &li);
-    if (!stream) cudaEventRecord(e->ev1, st);
+    if (!stream) { cudaEventRecord(e->ev1, st); e->ev_recorded = true; }
     return finish_launch(e, err, li);
 } CLK_GUARD_INT(e)
 
@@ -914,9 +914,11 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
         if (offs16) {                                      // keep a chunk under 256 MiB of payload
             const uint64_t cap16 = (256ull << 20) / 16;
             while (cnt > 1 && (uint64_t)(offs16[done + cnt] - offs16[done]) > cap16) cnt /= 2;
-            // offsets must be monotonic (the kernel trusts them); checked per chunk so it overlaps earlier chunks' copies
-            for (uint64_t i = done; i < done + cnt; i++)
-                if (offs16[i + 1] < offs16[i]) return fail(e, CLK_EINVAL, "offs16 not monotonic at %llu", (unsigned long long)i);
+            // the chunk's byte range must lie inside the caller's blob before anything is copied from it
+            if (offs16[done + cnt] < offs16[done] || offs16[done + cnt] > offs16[n]) {
+                for (int q = 0; q < 3; q++) cudaStreamSynchronize(e->pipe[q]);      // earlier chunks still copy into the caller's verdicts: finish them before returning
+                return fail(e, CLK_EINVAL, "offs16 not monotonic in [%llu, %llu]", (unsigned long long)done, (unsigned long long)(done + cnt));
+            }
         }
         int s = k % 3; cudaStream_t st = e->pipe[s];
         CUDA_TRY(e, cudaStreamSynchronize(st));            // buffers of this lane are free again
@@ -929,6 +931,16 @@ static int classify_host(clk_engine *e, const uint8_t *pkts, const uint32_t *off
             // offsets first: if they sit in pageable memory the (blocking, staged) copy is short and does not wait behind the frames
             CUDA_TRY(e, cudaMemcpyAsync(e->work_offs[s].p, offs16 + done, (cnt + 1) * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(e, cudaMemcpyAsync(e->work_pkts[s].p, pkts + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+            // offsets must be monotonic (the kernel trusts them): checked while this chunk's copies are on the wire, before its launch
+            {
+                uint32_t bad = 0;
+                const uint32_t *o = offs16 + done;
+                for (uint64_t i = 0; i < cnt; i++) bad |= (uint32_t)(o[i + 1] < o[i]);
+                if (bad) {
+                    for (int q = 0; q < 3; q++) cudaStreamSynchronize(e->pipe[q]);      // nothing of ours touches the caller's buffers after we return
+                    for (uint64_t i = 0; i < cnt; i++) if (o[i + 1] < o[i]) return fail(e, CLK_EINVAL, "offs16 not monotonic at %llu", (unsigned long long)(done + i));
+                }
+            }
             // offsets stay absolute: bias the base pointer instead of rewriting them
             const VarlenCtx *vc = nullptr;
             rc = varlen_ctx(e, st, cnt, &vc); if (rc) return rc;
@@ -1344,8 +1356,10 @@ int clk_get_stats(clk_engine *e, clk_stats *out)
 try {
     if (!e || !out) return fail(e, CLK_EINVAL, "NULL");
     std::lock_guard<std::mutex> g(e->mu);
-    if (!e->host_only && e->stats.kernel_launches && e->ev0 && cudaEventQuery(e->ev1) == cudaSuccess) {
-        float ms = 0; if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->stats.last_kernel_ms = ms;
+    if (!e->host_only && e->ev_recorded) {      // (the elapsed time of never-recorded events is an API error, and any error here would sit in
+        float ms = 0;                          //  the runtime's last-error slot for the next launch check to find: clear what this call raises)
+        if (cudaEventQuery(e->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->stats.last_kernel_ms = ms;
+        else cudaGetLastError();
     }
     *out = e->stats;
     return CLK_OK;

@@ -105,3 +105,43 @@ def test_dev_entries_on_two_streams_do_not_share_scratch():
         e.classify_slots_dev(db.data_ptr(), 64, b.shape[0], 0, vb.data_ptr(), s2.cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(va.cpu().numpy().view(np.uint32), wa) and np.array_equal(vb.cpu().numpy().view(np.uint32), wb)
+
+
+@pytest.mark.gpu
+def test_stats_before_any_timed_launch_leaves_no_pending_cuda_error():
+    """clk_get_stats used to ask for the elapsed time of events that had never been recorded (host-buffer and caller-stream paths do
+    not record them): an API error that stayed in the runtime's last-error slot until the next launch check (found by compute-sanitizer)."""
+    import torch
+    w = capture.make_workload("c2")
+    pk = capture.gen_slots(w, 4096, seed=1)
+    e = engine.Engine()
+    e.load_tables(w.tables)
+    e.publish()
+    e.classify_slots(pk, 64, 0)                       # host path: no timing events
+    assert e.stats().kernel_launches >= 1
+    cudart = torch.cuda.cudart()
+    assert int(cudart.cudaGetLastError()) == 0 if hasattr(cudart, "cudaGetLastError") else True
+    e.classify_slots(pk, 64, 0)                       # and the next launch check does not trip over a stale error
+    e.close()
+
+
+@pytest.mark.gpu
+def test_varlen_host_path_rejects_bad_offsets(monkeypatch):
+    """The host-buffer varlen path copies chunk by chunk and checks a chunk's offsets while its copy is on the wire: a dip inside a
+    chunk, or a chunk boundary outside the blob, is CLK_EINVAL — and nothing is read past the caller's blob."""
+    monkeypatch.setenv("CLK_CHUNK_PKTS", "1024")
+    w = capture.make_workload("c3")
+    blob, offs = capture.gen_varlen(w, 5000, seed=4)[:2]
+    e = engine.Engine()
+    e.load_tables(w.tables)
+    e.publish()
+    good = e.classify_varlen(blob, offs, abi.F_NAME_STAGE)
+    assert good.size == 5000
+    for at, val in ((2500, None), (1024, 0xFFFFFFF0), (2048, 0)):
+        bad = offs.copy()
+        bad[at] = (bad[at + 1] + 7) if val is None else val          # a dip at `at` + 1, a boundary far outside the blob, a boundary below the chunk's start
+        with pytest.raises(engine.ClkError) as ei:
+            e.classify_varlen(blob, bad, abi.F_NAME_STAGE)
+        assert ei.value.code == abi.EINVAL and "monotonic" in str(ei.value)
+    assert np.array_equal(e.classify_varlen(blob, offs, abi.F_NAME_STAGE), good)      # the engine is still usable
+    e.close()
