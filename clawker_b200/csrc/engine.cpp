@@ -28,6 +28,7 @@
 #include <nccl.h>          // types and prototypes only: the library is dlopen()ed by clk_comm_init, never linked
 
 #include "../../include/clawker_gpu.h"
+#include "hdr16_pack.h"
 #include "classify.h"
 #include "dev_tables.h"
 #include "rules.h"
@@ -980,15 +981,8 @@ try {
     uint64_t na = 0;
     for (uint64_t i = 0; i < n; i++) {
         const uint8_t *p = pkts + i * stride;
-        clk_hdr16 r; memset(&r, 0, sizeof r);
-        const bool ipv4 = p[12] == 0x08 && p[13] == 0x00, ipv6 = p[12] == 0x86 && p[13] == 0xDD;
-        if (ipv4 && p[14] == 0x45 && ((p[20] & 0x1f) | p[21]) == 0) {          // IHL 5, fragment offset 0 (same test as fast_classify)
-            r.kind = CLK_HDR_IPV4; r.proto = p[23];
-            memcpy(&r.src, p + 26, 4); memcpy(&r.dst, p + 30, 4);
-            r.sport = (uint16_t)((p[34] << 8) | p[35]); r.dport = (uint16_t)((p[36] << 8) | p[37]);
-        } else if (!ipv4 && !ipv6) {
-            r.kind = CLK_HDR_NONE;
-        } else {
+        clk_hdr16 r;
+        if (clk_hdr16_from_frame(p, r)) {
             if (!aux || na >= aux_cap) return fail(nullptr, CLK_E2BIG, "aux holds %llu slots, more frames need one", (unsigned long long)aux_cap);
             if (na > 0xffffffffull) return fail(nullptr, CLK_E2BIG, "more than 2^32 aux slots");
             memcpy(aux + na * 64, p, 64);

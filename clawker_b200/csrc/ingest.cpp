@@ -28,6 +28,7 @@
 #include <unistd.h>
 
 #include "../../include/clawker_gpu.h"
+#include "hdr16_pack.h"
 
 namespace {
 thread_local std::string tl_ingest_error;
@@ -135,6 +136,51 @@ try {
     }
     offs16[n] = (uint32_t)(used / 16);
     *n_frames = n; r->frames += n;
+    return CLK_OK;
+} ING_GUARD
+
+/* The same drain, but straight into compact ingest records (clk_hdr16, + 64-byte aux slots for the frames a record cannot express):
+ * what clk_classify_hdr16 takes, 16 bytes per frame over the host link.  Stops when recs or aux is full (the block is resumed by the
+ * next call).  No payload leaves the ring on this path: no name stage. */
+int clk_afpacket_read_hdr16(clk_ring *r, clk_hdr16 *recs, uint64_t cap_frames, uint8_t *aux, uint64_t aux_cap, int timeout_ms,
+                            uint64_t *n_frames, uint64_t *n_aux)
+try {
+    if (!r || !recs || !n_frames || !n_aux || (aux_cap && !aux)) return ifail(CLK_EINVAL, "NULL");
+    uint64_t n = 0, na = 0; bool waited = false;
+    while (n < cap_frames) {
+        struct tpacket_block_desc *bd = (struct tpacket_block_desc *)(r->map + (size_t)r->cur * r->block_size);
+        if (!(bd->hdr.bh1.block_status & TP_STATUS_USER)) {
+            if (n || waited) break;
+            struct pollfd pfd = { r->fd, POLLIN | POLLERR, 0 };
+            waited = true;
+            if (poll(&pfd, 1, timeout_ms) <= 0) break;
+            continue;
+        }
+        if (!r->pkt_ptr) { r->pkt_in_block = 0; r->pkt_ptr = (uint8_t *)bd + bd->hdr.bh1.offset_to_first_pkt; }
+        const uint32_t num = bd->hdr.bh1.num_pkts;
+        bool full = false;
+        while (r->pkt_in_block < num) {
+            const struct tpacket3_hdr *ph = (const struct tpacket3_hdr *)r->pkt_ptr;
+            if (n >= cap_frames) { full = true; break; }
+            uint8_t head[64];
+            const uint32_t take = ph->tp_snaplen < 64 ? ph->tp_snaplen : 64;
+            memcpy(head, r->pkt_ptr + ph->tp_mac, take); if (take < 64) memset(head + take, 0, 64 - take);
+            clk_hdr16 rec;
+            if (clk_hdr16_from_frame(head, rec)) {
+                if (na >= aux_cap || na > 0xffffffffull) { full = true; break; }
+                memcpy(aux + na * 64, head, 64);
+                rec.kind = CLK_HDR_AUX; rec.src = (uint32_t)na++;
+            }
+            recs[n++] = rec;
+            r->pkt_in_block++;
+            if (!ph->tp_next_offset) r->pkt_in_block = num; else r->pkt_ptr += ph->tp_next_offset;
+        }
+        if (full) break;
+        bd->hdr.bh1.block_status = TP_STATUS_KERNEL;
+        __sync_synchronize();
+        r->pkt_ptr = nullptr; r->cur = (r->cur + 1) % r->block_nr;
+    }
+    *n_frames = n; *n_aux = na; r->frames += n;
     return CLK_OK;
 } ING_GUARD
 

@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
         "clk_pcap_last_error": (C.c_char_p, []),
         "clk_afpacket_open": (i32, [C.c_char_p, u32, C.POINTER(vp)]),
         "clk_afpacket_read": (i32, [vp, vp, u64, vp, u64, i32, C.POINTER(u64)]),
+        "clk_afpacket_read_hdr16": (i32, [vp, vp, u64, vp, u64, i32, C.POINTER(u64), C.POINTER(u64)]),
         "clk_afpacket_close": (i32, [vp]),
         "clk_tcp_coalesce": (i32, [vp, vp, u64, vp, u64, vp, C.POINTER(u64)]),
         "clk_ingest_last_error": (C.c_char_p, []),
@@ -126,7 +127,7 @@ EXPORTS = ["clk_abi_version", "clk_strerror", "clk_last_error", "clk_engine_crea
            "clk_classify_varlen", "clk_classify_slots_dev", "clk_classify_varlen_dev", "clk_classify_events", "clk_pack_hdr16", "clk_classify_hdr16", "clk_classify_hdr16_dev",
            "clk_dns_answers", "clk_counters_read", "clk_counters_read_global", "clk_counters_reset", "clk_counters_block_rows",
            "clk_counters_export", "clk_counters_import", "clk_totals_rows", "clk_totals_export", "clk_totals_merge", "clk_comm_unique_id", "clk_comm_init", "clk_comm_destroy", "clk_comm_info",
-           "clk_allgather_counters", "clk_totals_read_global", "clk_allgather_metrics", "clk_state_save", "clk_state_load", "clk_pcap_pack", "clk_classify_pcap", "clk_pcap_last_error", "clk_afpacket_open", "clk_afpacket_read", "clk_afpacket_close", "clk_tcp_coalesce", "clk_ingest_last_error", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
+           "clk_allgather_counters", "clk_totals_read_global", "clk_allgather_metrics", "clk_state_save", "clk_state_load", "clk_pcap_pack", "clk_classify_pcap", "clk_pcap_last_error", "clk_afpacket_open", "clk_afpacket_read", "clk_afpacket_read_hdr16", "clk_afpacket_close", "clk_tcp_coalesce", "clk_ingest_last_error", "clk_get_stats", "clk_sync", "clk_host_alloc", "clk_host_free"]
 
 
 class PacketRing:
@@ -144,6 +145,16 @@ class PacketRing:
         if rc:
             raise ClkError(rc, self.L.clk_ingest_last_error().decode())
         return blob[: int(offs[n.value]) * 16], offs[: n.value + 1]
+
+    def read_hdr16(self, cap_frames: int = 1 << 16, aux_cap: int = 4096, timeout_ms: int = 100):
+        """(recs, aux) for Engine.classify_hdr16: compact ingest records straight from the ring."""
+        from .abi import HDR16_DTYPE
+        recs, aux = np.zeros(cap_frames, dtype=HDR16_DTYPE), np.zeros(aux_cap * 64, dtype=np.uint8)
+        n, na = C.c_uint64(), C.c_uint64()
+        rc = self.L.clk_afpacket_read_hdr16(self.h, recs.ctypes.data, cap_frames, aux.ctypes.data, aux_cap, timeout_ms, C.byref(n), C.byref(na))
+        if rc:
+            raise ClkError(rc, self.L.clk_ingest_last_error().decode())
+        return recs[: n.value], aux[: na.value * 64]
 
     def close(self):
         if self.h:

@@ -411,6 +411,24 @@ func (r *Ring) Read(blob []byte, offs16 []uint32, timeoutMs int) (int, error) {
 	return int(n), nil
 }
 
+// ReadHdr16 drains ready blocks straight into compact ingest records (+ 64-byte aux slots): input of ClassifyHdr16.
+func (r *Ring) ReadHdr16(recs []Hdr16, aux []byte, timeoutMs int) (n, nAux int, err error) {
+	if len(recs) == 0 {
+		return 0, 0, fmt.Errorf("clawker_gpu: empty buffers")
+	}
+	var cn, ca C.uint64_t
+	var pa *C.uint8_t
+	if len(aux) > 0 {
+		pa = (*C.uint8_t)(unsafe.Pointer(&aux[0]))
+	}
+	rc := C.clk_afpacket_read_hdr16(r.h, (*C.clk_hdr16)(unsafe.Pointer(&recs[0])), C.uint64_t(len(recs)), pa, C.uint64_t(len(aux)/64),
+		C.int(timeoutMs), &cn, &ca)
+	if rc != C.CLK_OK {
+		return 0, 0, fmt.Errorf("clawker_gpu: %s (%d)", C.GoString(C.clk_ingest_last_error()), int(rc))
+	}
+	return int(cn), int(ca), nil
+}
+
 func (r *Ring) Close() { C.clk_afpacket_close(r.h); r.h = nil }
 
 // TCPCoalesce folds the continuation segments of split ClientHellos / HTTP request heads into their first segment

@@ -445,6 +445,10 @@ typedef struct clk_ring clk_ring;
 int clk_afpacket_open(const char *ifname, uint32_t ring_mib, clk_ring **out);
 int clk_afpacket_read(clk_ring *r, uint8_t *blob, uint64_t cap_bytes, uint32_t *offs16,
                       uint64_t cap_frames, int timeout_ms, uint64_t *n_frames);
+/* The same drain straight into compact ingest records (clk_hdr16 + 64-byte aux slots, what clk_classify_hdr16 takes): the frames
+ * never leave the ring whole, 16 bytes per frame cross the host link.  Stops when recs or aux is full. */
+int clk_afpacket_read_hdr16(clk_ring *r, clk_hdr16 *recs, uint64_t cap_frames, uint8_t *aux, uint64_t aux_cap,
+                            int timeout_ms, uint64_t *n_frames, uint64_t *n_aux);
 int clk_afpacket_close(clk_ring *r);
 /* TCP reassembly for the name stage.  Envoy's tls_inspector and HTTP codec buffer a connection until
  * the ClientHello / request head is complete (envoy.go:299-306 listener filters); a per-packet

@@ -201,3 +201,50 @@ def test_gpu_classifies_the_coalesced_batch():
     got = e.classify_varlen(out, oo, flags=F)
     assert np.array_equal(got, _orc(out, oo))
     e.close()
+
+
+def test_afpacket_ring_to_hdr16_records():
+    """The ring drained straight into compact ingest records: same records as packing the captured frames (clk_pack_hdr16)."""
+    try:
+        ring = engine.PacketRing("lo", ring_mib=4)
+        ring2 = engine.PacketRing("lo", ring_mib=4)
+    except engine.ClkError as x:
+        pytest.skip(f"AF_PACKET not available here: {x}")
+    with ring, ring2:
+        s = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        s6 = socket.socket(socket.AF_INET6, socket.SOCK_DGRAM)
+        tag = b"clawker-h16-%d-" % time.time_ns()
+        for i in range(200):
+            s.sendto(tag + b"%04d" % i, ("127.0.0.1", 40054))
+            if i % 10 == 0:
+                try:
+                    s6.sendto(tag + b"v6%02d" % i, ("::1", 40054))      # IPv6 frames: aux slots
+                except OSError:
+                    pass
+        s.close(); s6.close()
+        time.sleep(0.1)
+        frames, recs, auxs, deadline = [], [], [], time.time() + 5
+        while time.time() < deadline:
+            blob, offs = ring.read(cap_bytes=1 << 20, cap_frames=4096, timeout_ms=100)
+            r, a = ring2.read_hdr16(cap_frames=4096, aux_cap=64, timeout_ms=100)
+            frames += [bytes(blob[int(offs[i]) * 16:int(offs[i + 1]) * 16]) for i in range(offs.size - 1)]
+            base = sum(x.size // 64 for x in auxs)
+            r = r.copy()
+            r["src"][r["kind"] == 2] += base                                   # CLK_HDR_AUX: slot index within this call -> within the run
+            recs.append(r); auxs.append(a)
+            if offs.size == 1 and r.size == 0 and frames:
+                break
+        recs, aux = np.concatenate(recs), np.concatenate(auxs) if auxs else np.zeros(0, np.uint8)
+        # the two rings may differ by unrelated loopback traffic around their opening: compare what this test sent
+        mine = [i for i, fr in enumerate(frames) if len(fr) >= 64 and fr[12:14] == b"\x08\x00" and fr[23] == 17 and fr[36:38] == (40054).to_bytes(2, "big")]
+        assert len(mine) == 200
+        slots = np.zeros((len(mine), 64), np.uint8)
+        for k, i in enumerate(mine):
+            slots[k] = np.frombuffer(frames[i][:64], np.uint8)
+        want, _ = engine.pack_hdr16(slots.reshape(-1), 64)                    # the host packer on the same frames
+        got = recs[(recs["kind"] == 0) & (recs["proto"] == 17) & (recs["dport"] == 40054)]
+        assert np.array_equal(got, want)
+        n6 = sum(1 for fr in frames if fr[12:14] == b"\x86\xdd")
+        assert int((recs["kind"] == 2).sum()) == aux.size // 64 >= min(n6, 1)
+        for j in np.flatnonzero(recs["kind"] == 2)[:8]:                       # an aux slot holds the frame's first 64 bytes
+            assert bytes(aux[int(recs["src"][j]) * 64:][:14]) [12:14] in (b"\x86\xdd", b"\x08\x00")
