@@ -159,6 +159,14 @@ def test_afpacket_ring_on_loopback():
                 if fr[12:14] == b"\x08\x00" and fr[23] == 17 and fr[42:42 + len(tag)] == tag:
                     seen.append(fr[42:14 + int.from_bytes(fr[16:18], "big")])
         assert seen == sent                                                  # every datagram once, in order, bytes intact
+        s = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        s.sendto(b"x" * 1000, ("127.0.0.1", 40053))
+        s.close()
+        time.sleep(0.05)
+        with pytest.raises(engine.ClkError) as big:                          # a frame that fits no buffer is an error, not an endless n == 0
+            ring.read(cap_bytes=256, cap_frames=8, timeout_ms=200)
+        assert big.value.code == abi.E2BIG
+        assert ring.read(cap_bytes=1 << 16, cap_frames=8, timeout_ms=200)[1].size >= 2       # ... and the frame is still there for a larger one
         w = _orc(blob, offs, 0)                                              # and the chunks are valid classifier input
         assert w.size == offs.size - 1
 
