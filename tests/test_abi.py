@@ -86,6 +86,22 @@ def test_manager_enable_disable_bypass(eng):
         m.SyncRoutes([ebpf.Route(i, 1, 2) for i in range(3)])                        # > max_entries
 
 
+def test_delete_errors_other_than_missing_key_surface(eng):
+    """TestClearBypass_IgnoresMissingEntry / _WrapsOtherErrors and TestDeleteExpiredDNSEntries_EmptyReturnsZero
+    (internal/ebpf/manager_test.go:216-270, 344-354): a missing key is success, anything else is an error that is NOT the
+    key-not-exist code — so a caller cannot mistake a failed clear for a cleared flag."""
+    m = ebpf.Manager(engine=eng)
+    assert eng.map_delete(abi.MAP_BYPASS, C.c_uint64(456)) == abi.ENOENT             # never set: the common case, silent
+    m.Unbypass(456)
+    with pytest.raises(engine.ClkError) as ei:                                       # a key of the wrong size (EINVAL from the map)
+        eng._ck(eng.L.clk_map_delete(eng.h, abi.MAP_BYPASS, C.byref(C.c_uint32(1)), 4), ok=(0, abi.ENOENT))
+    assert ei.value.code == abi.EINVAL and ei.value.code != abi.ENOENT
+    with pytest.raises(engine.ClkError) as ei:                                       # no such map
+        eng._ck(eng.L.clk_map_delete(eng.h, 99, C.byref(C.c_uint64(1)), 8), ok=(0, abi.ENOENT))
+    assert ei.value.code != abi.ENOENT
+    assert m.GarbageCollectDNS(now=10**9) == 0                                       # nothing expired, nothing touched
+
+
 def test_no_cpu_fallback(eng):
     import numpy as np
     for call in (lambda: eng.publish(), lambda: eng.classify_slots(np.zeros((4, 64), np.uint8)),
