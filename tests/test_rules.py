@@ -213,3 +213,22 @@ def test_product_equals_oracle_on_random_rule_sets(eng, seed):
         got_http.append((d.split(","), [(x[1:], x[0] == "A") for x in rt.split(",")]))
     assert got_http == [(d, r) for d, r in o.http]
     assert sorted(eng.map_rows(7)) == sorted(int(a).to_bytes(4, "little") + int(m).to_bytes(4, "little") for a, m in set(o.cidrs))
+
+
+def test_product_rule_normalisation_defaults(eng):
+    """normalizeRule + ruleKey as the reference's rule store applies them before anything is generated
+    (internal/firewall/rules.go:113-132; TestAddRules_DefaultProto / _NormalizesEmptyFields / _Deduplication /
+    _DifferentPortsNotDuplicate, rules_test.go:62-102,236-258): an empty proto is tls, an empty action allow, a tls rule
+    without a port is 443; explicit values are never overridden; the dedup key is dst:proto:port."""
+    R = firewall.EgressRule
+    c = firewall.compile_rules(eng, [R("a.com"), R("b.com", "ssh", 22)])
+    assert "a.com" in c.server_names and "a.com" in c.zones                      # proto -> tls, action -> allow, port -> 443
+    assert c.tcp_mappings == [("b.com", 22, 10001)] and "b.com" not in c.server_names      # ssh:22 stays what it is
+    same = firewall.compile_rules(eng, [R("a.com"), R("a.com", "tls", 443, "allow"), R("a.com", "tls", 0, "")])
+    assert same.server_names.count("a.com") == 1 and same.zones.count("a.com") == 1        # one rule after normalisation
+    two = firewall.compile_rules(eng, [R("example.com", "tcp", 80, "allow"), R("example.com", "tcp", 443, "allow")])
+    assert [(d, p) for d, p, _ in two.tcp_mappings] == [("example.com", 80), ("example.com", 443)]   # different ports are different rules
+    assert len({ep for _, _, ep in two.tcp_mappings}) == 2
+    # the oracle's restatement says the same
+    o = ro.compile_rules([{"dst": "a.com"}, {"dst": "a.com", "proto": "tls", "port": 443, "action": "allow"}, {"dst": "b.com", "proto": "ssh", "port": 22}])
+    assert list(o.snis).count("a.com") == 1 and [tuple(m)[:2] for m in o.mappings] == [("b.com", 22)]
