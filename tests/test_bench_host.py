@@ -210,3 +210,47 @@ def test_run_gpu_flow_multi_and_varlen(monkeypatch, capsys):
     assert d["n_gpus"] == 2 and d["gpu_launches"] == 8 and "4 SMs reserved" in d["config"]["collective"]     # classify + totals per step
     d = _dry_run(monkeypatch, capsys, 1, "c3h")
     assert "k_varlen_head" in d["roofline"]["kernel"] and "e2e_compact" not in d and d["config"]["layout"].startswith("varlen")
+
+
+# ---- bench.check_parity on CPU: does the checker itself catch a wrong word, a wrong copy, a wrong counter? -------------
+class _ParityEngine:
+    def __init__(self, rows, dropped=0):
+        self.rows, self.dropped = rows, dropped
+
+    def counters_reset(self): pass
+    def counters(self): return self.rows
+
+    def stats(self):
+        s = _FakeStats()
+        s.metrics_dropped = self.dropped
+        return s
+
+
+def test_check_parity_catches_words_copies_and_counters(monkeypatch):
+    import numpy as np
+    import torch
+    from clawker_b200 import capture
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    w = capture.make_workload("c2")
+    gen, reps = 20_000, 3
+    pk = capture.gen_slots(w, gen, seed=9)
+    o, _ = bench._oracle_for(w, False, want_cidr=True)
+    want, wm = o.classify(pk, None, flags=0)
+    rows = wm.copy()
+    rows["count"] *= reps                                     # what a correct engine holds after one pass over the tiled batch
+    good = torch.from_numpy(np.tile(want, reps).view(np.int32).copy())
+    args = dict(w=w, batch=(pk, None), n=gen * reps, gen=gen, varlen=False, flags=0, run_step=lambda: None, threads=2)
+    p = bench.check_parity(_ParityEngine(rows), d_v=good, **args)
+    assert p["mismatches"] == 0 and p["copy_mismatches"] == 0 and p["copies_checked"] == reps and p["rate"] == 1.0
+    assert p["counters"] == {"rows": int(wm.size), "oracle_rows": int(wm.size), "mismatches": 0}
+    bad = good.clone(); bad[5] ^= 1                           # a wrong word in the first copy: the oracle comparison sees it (and every other copy now differs from it)
+    p = bench.check_parity(_ParityEngine(rows), d_v=bad, **args)
+    assert p["mismatches"] == 1 and p["copy_mismatches"] == reps - 1 and p["rate"] < 1.0
+    bad = good.clone(); bad[gen + 7] ^= 4                     # a wrong word in the MIDDLE copy: only the device-side copy comparison can see it
+    p = bench.check_parity(_ParityEngine(rows), d_v=bad, **args)
+    assert p["mismatches"] == 0 and p["copy_mismatches"] == 1 and p["rate"] < 1.0
+    r2 = rows.copy(); r2["count"][3] += 1                     # one increment too many
+    assert bench.check_parity(_ParityEngine(r2), d_v=good, **args)["counters"]["mismatches"] == 1
+    r3 = np.concatenate([rows, rows[:1]]); r3["dst_port"][-1] ^= 0x5555        # a stray row (what a header read after a TMA refill produced in round 2)
+    assert bench.check_parity(_ParityEngine(r3), d_v=good, **args)["counters"]["mismatches"] >= 1
+    assert "skipped" in bench.check_parity(_ParityEngine(rows, dropped=5), d_v=good, **args)["counters"]
