@@ -203,6 +203,11 @@ def test_run_gpu_flow_single(monkeypatch, capsys):
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["clocks"]["reasons"] == ["unavailable"]
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] == 8192 * 64
     assert d["e2e_compact"]["h2d_bytes_per_step"] == 8192 * 16 and d["e2e_compact"]["bytes_per_packet_over_pcie"] == 20.0
+    # the arithmetic of the line, with the fake events' 0.25 ms between any two records: 4 timed steps take 0.25 ms in all
+    assert d["ms_per_step"] == 0.0625 and d["value"] == round(8192 / 0.0625 / 1e3, 1)
+    r = d["roofline"]
+    assert r["algorithmic_bytes_per_packet"] == 68.0 and r["kernel_ms"] == 0.25                   # one classify call per step, 0.25 ms each
+    assert abs(r["achieved"] - 8192 * 68 / 0.25e-3 / 1e9) < 0.06 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and r["bound"] == "hbm" and r["unit"] == "GB/s"
 
 
 def test_run_gpu_flow_multi_and_varlen(monkeypatch, capsys):
